@@ -1,0 +1,20 @@
+"""geocalib_b200 -- a Blackwell-native (sm_100a) Levenberg-Marquardt calibration engine that drops
+in behind cvg/GeoCalib's `LMOptimizer` / `Camera` / `Gravity` API.
+
+    from geocalib_b200 import LMOptimizer, install
+    install(reference_geocalib_model)            # attribute swap of model.optimizer
+    out = LMOptimizer({"camera_model": "pinhole"}).eval()(fields_on_cuda)
+
+The hot path lives in `csrc/` (CUDA + C ABI, built to csrc/libgclm.so); importing the package does
+not need a GPU, running the optimizer does.  There is no CPU fallback.
+"""
+
+from .camera import BaseCamera, Pinhole, Radial, SimpleDivisional, SimpleRadial, camera_models
+from .gravity import Gravity
+from .lm_optimizer import B200LMOptimizer, LMOptimizer, get_trivial_estimation, install
+
+__all__ = [
+    "BaseCamera", "Pinhole", "Radial", "SimpleDivisional", "SimpleRadial", "camera_models",
+    "Gravity", "LMOptimizer", "B200LMOptimizer", "get_trivial_estimation", "install",
+]
+__version__ = "0.1.0"

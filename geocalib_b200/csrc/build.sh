@@ -1,0 +1,7 @@
+#!/bin/bash
+# Builds libgclm.so for sm_100a in-tree (the .so is git-ignored but travels with gpurun).
+set -e
+cd "$(dirname "$0")"
+NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
+$NVCC -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo \
+  -Xcompiler -fPIC -Xcompiler -Wall -shared -o libgclm.so gclm_engine.cu -ldl "$@"

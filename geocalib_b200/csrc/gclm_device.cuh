@@ -1,0 +1,479 @@
+// gclm_device.cuh -- per-pixel perspective-field math and the per-image LM solver (device code).
+//
+// Written from the closed form in SURVEY.md Appendix A (verified there against the reference's
+// setup_system in fp64) -- NOT a translation of the reference's tensor program.  Reference
+// functions each block replaces are cited as geocalib/<file>:<lines>.
+//
+// Algebra used by the kernel (and independently checked by oracle/gclm_oracle.c, which follows
+// the reference's explicit 2x2 / 3x2 Jacobian chain instead):
+//   * In 2-D, I - n n^T = n_perp n_perp^T, so every column of the up-field Jacobian
+//     J_vecnorm(p) z  (misc.py:262-281) is  n_perp * (n_perp . z) / |p|.  The Gauss-Newton
+//     system therefore only needs the scalars  s_j = (n_perp . z_j)/|p|  and the scalar
+//     residual e = n_perp . up_obs:   J^T W J += w s s^T,   J^T W r += w s e.
+//   * The Huber weight still uses the full 2-vector residual (lm_optimizer.py:291-293).
+//   * sin(asin(clamp(l))) == clamp(l)  (perspective_fields.py:208-209 + lm_optimizer.py:262).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace gclm {
+
+enum : int { PINHOLE = 0, SIMPLE_RADIAL = 1, RADIAL = 2, SIMPLE_DIVISIONAL = 3 };
+
+__host__ __device__ constexpr int num_dist(int model) {
+  return model == PINHOLE ? 0 : (model == RADIAL ? 2 : 1);
+}
+template <int MODEL>
+struct Dims {
+  static constexpr int K = num_dist(MODEL);
+  static constexpr int NF = 3 + K;                // full columns: g0 g1 f k..
+  static constexpr int NH = NF * (NF + 1) / 2;    // upper triangle of J^T W J
+  static constexpr int NACC = NH + NF + 2;        // + J^T W r + two cost sums
+};
+constexpr int MAX_NF = 5;
+constexpr int MAX_NACC = 15 + 5 + 2;
+
+// ------------------------------------------------------------------------------------------
+// fast hardware approximations used in the streaming pass only
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float fast_rsqrt(float x) {
+  float y;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float fast_rcp(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// sin(x) for |x| <= 1.6 (latitudes live in [-pi/2, pi/2]): degree-9 odd polynomial, max abs
+// error 1.5e-7 against fp64 sin (coefficients: Chebyshev fit of (sin(x)/x - 1)/x^2 in x^2).
+__device__ __forceinline__ float sin_poly(float x) {
+  const float z = x * x;
+  float p = 2.6303815071e-06f;
+  p = fmaf(p, z, -1.9821368161e-04f);
+  p = fmaf(p, z, 8.3332318302e-03f);
+  p = fmaf(p, z, -1.6666665857e-01f);
+  return fmaf(x * z, p, x);
+}
+// Cold path: any of the four latitudes is outside the polynomial's range -> exact sinf for all.
+__device__ __noinline__ void sin4_slow(const float4 x, float (&s)[4]) {
+  s[0] = sinf(x.x); s[1] = sinf(x.y); s[2] = sinf(x.z); s[3] = sinf(x.w);
+}
+// target_lat = sin(latitude_field) for 4 pixels (lm_optimizer.py:270)
+__device__ __forceinline__ void sin4(const float4 x, float (&s)[4]) {
+  s[0] = sin_poly(x.x); s[1] = sin_poly(x.y); s[2] = sin_poly(x.z); s[3] = sin_poly(x.w);
+  const float mx = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));
+  if (mx > 1.6f) sin4_slow(x, s);
+}
+
+// ------------------------------------------------------------------------------------------
+// per-image constants of one pass (hoisted out of the pixel loop)
+// ------------------------------------------------------------------------------------------
+struct PassConst {
+  float inv_fx, inv_fy, cx, cy;
+  float a, b, c;                     // gravity (unit)
+  float T00, T01, T10, T11, T20, T21; // tangent basis (3x2): spherical or (roll,pitch)
+  float dsx, dsy;                    // focal direction d = (-u dsx, -v dsy): 1,1 (log) or 1/fx,1/fy
+  float k1, k2;
+};
+
+// ---- gravity helpers: geocalib/misc.py:181-259, geocalib/gravity.py:62-101 ----
+__device__ inline void householder(const float g[3], float hv[3], float& beta) {
+  float sigma = g[0] * g[0] + g[1] * g[1];
+  const float xpiv = g[2];
+  const float nrm = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+  if (sigma < 1e-7f) sigma += 1e-7f;  // misc.py:202-204
+  const float vpiv = xpiv < 0.f ? xpiv - nrm : -sigma / (xpiv + nrm);
+  beta = 2.f * vpiv * vpiv / (sigma + vpiv * vpiv);
+  hv[0] = g[0] / vpiv; hv[1] = g[1] / vpiv; hv[2] = 1.f;
+}
+
+__device__ inline void gravity_rp(const float g[3], float& roll, float& pitch) {
+  // gravity.py:15,62-67: note the 1e-4 eps in the roll read-back
+  const float r = asinf(-g[0] / (sqrtf(1.f - g[2] * g[2]) + 1e-4f));
+  const float sgn = g[0] > 0.f ? 1.f : (g[0] < 0.f ? -1.f : 0.f);
+  roll = g[1] < 0.f ? r : -r - 3.14159265358979323846f * sgn;
+  pitch = asinf(g[2]);
+}
+
+__device__ inline void normalize3(float g[3]) {  // F.normalize, eps 1e-12 (gravity.py:26)
+  const float n = fmaxf(sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]), 1e-12f);
+  g[0] /= n; g[1] /= n; g[2] /= n;
+}
+
+// cam = [w h fx fy cx cy k1 k2], g unit.  rpf: use the (roll,pitch) basis and the non-log focal
+// direction (estimate_uncertainty -> setup_system(as_rpf=True), lm_optimizer.py:411-416,481-483).
+__device__ inline void make_pass_const(const float* cam, const float* g, bool spherical,
+                                       bool log_focal, bool rpf, PassConst& pc) {
+  pc.inv_fx = 1.f / cam[2]; pc.inv_fy = 1.f / cam[3];
+  pc.cx = cam[4]; pc.cy = cam[5]; pc.k1 = cam[6]; pc.k2 = cam[7];
+  pc.a = g[0]; pc.b = g[1]; pc.c = g[2];
+  if (spherical && !rpf) {  // SphericalManifold.J_plus: (I - beta v v^T)[:, :2]
+    float hv[3], beta;
+    householder(g, hv, beta);
+    pc.T00 = 1.f - beta * hv[0] * hv[0]; pc.T01 = -beta * hv[0] * hv[1];
+    pc.T10 = -beta * hv[1] * hv[0];      pc.T11 = 1.f - beta * hv[1] * hv[1];
+    pc.T20 = -beta * hv[2] * hv[0];      pc.T21 = -beta * hv[2] * hv[1];
+  } else {  // Gravity.J_rp (gravity.py:69-101)
+    float roll, pitch;
+    gravity_rp(g, roll, pitch);
+    float sr, cr, sp, cp;
+    sincosf(roll, &sr, &cr);
+    sincosf(pitch, &sp, &cp);
+    pc.T00 = -cr * cp; pc.T10 = sr * cp; pc.T20 = 0.f;
+    pc.T01 = sr * sp;  pc.T11 = cr * sp; pc.T21 = cp;
+  }
+  if (log_focal && !rpf) { pc.dsx = 1.f; pc.dsy = 1.f; }
+  else { pc.dsx = pc.inv_fx; pc.dsy = pc.inv_fy; }
+}
+
+// ------------------------------------------------------------------------------------------
+// camera-model scalars at one pixel
+//   distort scale s, offset o = phi*uv, J_o = A I + Bc uv uv^T, ds/dk = sk, do/dk = psi*uv,
+//   undistort scale su, d(su uv)/duv = su I + Q uv uv^T, d(su uv)/dk = om*uv
+// ------------------------------------------------------------------------------------------
+template <int K>
+struct ModelScalars {
+  float s, phi, A, Bc, su, Q;
+  float sk[K > 0 ? K : 1], psi[K > 0 ? K : 1], om[K > 0 ? K : 1];
+};
+
+// Literal restatement of SimpleDivisional with its masked denominators (camera.py:829-942).
+// Used only when the cancellation-free closed form does not apply: k1 == 0 (trivial init, the
+// masked branches make ds/dk = 0 and J_o = 2/r^2 I - 8/r^4 uv uv^T) or
+// 1 - 4 k1 r^2 < 1e-6 (clamped square root).  Cold path.
+__device__ __noinline__ void divisional_literal(float k1, float r2, ModelScalars<1>& m) {
+  auto mf = [](float d) { return d == 0.f ? 1e6f : d; };
+  const float x = 1.f - 4.f * k1 * r2;
+  const float rad = 1.f - sqrtf(fmaxf(x, 0.f));
+  const float den = 2.f * k1 * r2;
+  m.s = den == 0.f ? 1.f : rad / mf(den);
+  const float t0 = fmaxf(x, 1e-6f), t1 = sqrtf(t0), t32 = t0 * t1;
+  {
+    const float d1 = t1 * 2.f * r2, d2 = k1 * r2 * r2;
+    m.phi = (4.f * d2 - (1.f - t1) * d1) / mf(d1 * d2);
+  }
+  {
+    const float d1 = 2.f * k1 * t1, d2 = 2.f * r2 * k1 * k1;
+    m.sk[0] = (2.f * d2 - (1.f - t1) * d1) / mf(d1 * d2);
+  }
+  m.psi[0] = 16.f / mf(4.f * t32) - 2.f / mf(r2 * t1 * k1) + (1.f - t1) / mf((r2 * k1) * (r2 * k1));
+  m.A = 4.f / mf(2.f * r2 * t1) - (1.f - t1) / mf(k1 * r2 * r2);
+  m.Bc = -16.f / mf(4.f * t1 * r2 * r2) + (32.f * k1) / mf(4.f * r2 * t32) - 4.f / mf(r2 * r2 * t1) +
+         4.f * (1.f - t1) / mf(k1 * r2 * r2 * r2);
+  const float dn = 1.f + k1 * r2;
+  m.su = 1.f / mf(dn);
+  m.Q = -2.f * k1 / (mf(dn) * mf(dn));
+  m.om[0] = -r2 / mf(dn * dn);
+}
+
+template <int MODEL>
+__device__ __forceinline__ void model_scalars(const PassConst& pc, float r2,
+                                              ModelScalars<num_dist(MODEL)>& m) {
+  if constexpr (MODEL == PINHOLE) {  // camera.py:532-562
+    m.s = 1.f; m.phi = 0.f; m.A = 0.f; m.Bc = 0.f; m.su = 1.f; m.Q = 0.f;
+  } else if constexpr (MODEL == SIMPLE_RADIAL) {  // camera.py:611-660
+    m.s = fmaf(pc.k1, r2, 1.f);
+    m.phi = 2.f * pc.k1; m.A = m.phi; m.Bc = 0.f;
+    m.sk[0] = r2; m.psi[0] = 2.f;
+    m.su = fmaf(-pc.k1, r2, 1.f);
+    m.Q = -2.f * pc.k1;
+    m.om[0] = -r2;
+  } else if constexpr (MODEL == RADIAL) {  // camera.py:712-786
+    const float r4 = r2 * r2;
+    m.s = fmaf(pc.k2, r4, fmaf(pc.k1, r2, 1.f));
+    m.phi = fmaf(4.f * pc.k2, r2, 2.f * pc.k1); m.A = m.phi; m.Bc = 8.f * pc.k2;
+    m.sk[0] = r2; m.sk[1] = r4;
+    m.psi[0] = 2.f; m.psi[1] = 4.f * r2;
+    const float b1 = -pc.k1, b2 = fmaf(3.f * pc.k1, pc.k1, -pc.k2);
+    m.su = fmaf(b2, r4, fmaf(b1, r2, 1.f));
+    m.Q = fmaf(4.f * b2, r2, 2.f * b1);
+    m.om[0] = fmaf(6.f * pc.k1, r4, -r2);
+    m.om[1] = -r4;
+  } else {  // SIMPLE_DIVISIONAL, camera.py:829-942
+    const float x = fmaf(-4.f * pc.k1, r2, 1.f);
+    if (pc.k1 == 0.f || x < 1e-6f) {
+      divisional_literal(pc.k1, r2, m);
+    } else {
+      // With t = sqrt(1 - 4 k1 r^2), w = 1 + t and 1 - t = 4 k1 r^2 / w every masked quotient of
+      // the reference collapses to a cancellation-free form that is finite at r^2 = 0:
+      //   s = 2/w, phi = A = 8 k1/(t w^2), Bc = 32 k1^2 (1+3t)/(t^3 w^3),
+      //   ds/dk = 4 r^2/(t w^2), psi = 4 (1 + 2t - t^2)/(t^3 w^2).
+      const float it = fast_rsqrt(x), t = x * it, w = 1.f + t, iw = fast_rcp(w);
+      const float itw2 = it * iw * iw, it2 = it * it;
+      m.s = 2.f * iw;
+      m.phi = 8.f * pc.k1 * itw2; m.A = m.phi;
+      m.Bc = 32.f * pc.k1 * pc.k1 * fmaf(3.f, t, 1.f) * itw2 * it2 * iw;
+      m.sk[0] = 4.f * r2 * itw2;
+      m.psi[0] = 4.f * fmaf(t, 2.f - t, 1.f) * itw2 * it2;
+      const float su = fast_rcp(fmaf(pc.k1, r2, 1.f));
+      m.su = su;
+      m.Q = -2.f * pc.k1 * su * su;
+      m.om[0] = -r2 * su * su;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// one pixel: residuals, robust weights, Jacobian rows, accumulation
+//   acc layout: [H upper triangle row-major (NH)] [G (NF)] [cost_up] [cost_lat]
+//   GEN_D: general focal direction (non-log focal or the final as_rpf pass)
+//   flags: runtime presence of the inputs (compile-time true when FULL)
+// ------------------------------------------------------------------------------------------
+struct FieldMask { bool up, lat, up_conf, lat_conf; };
+
+template <int MODEL, bool GEN_D, bool FULL>
+__device__ __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMask fm, float u,
+                                                 float v, float ox, float oy, float sin_olat, float cu,
+                                                 float cl, float inv_up2, float inv_lat2,
+                                                 float (&acc)[Dims<MODEL>::NACC]) {
+  constexpr int K = Dims<MODEL>::K, NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH;
+  const bool has_up = FULL || fm.up, has_lat = FULL || fm.lat;
+  const float r2 = fmaf(u, u, v * v);
+  ModelScalars<K> m;
+  model_scalars<MODEL>(pc, r2, m);
+
+  float su_[NF], sl_[NF];  // Jacobian row scalars (up: along n_perp; latitude)
+  float e = 0.f, w_up = 0.f, r_lat = 0.f, w_lat = 0.f;
+  float dx = 0.f, dy = 0.f, uvd = 0.f;
+  if constexpr (GEN_D) { dx = -u * pc.dsx; dy = -v * pc.dsy; uvd = fmaf(u, dx, v * dy); }
+
+  if (has_up) {  // ---- up field: perspective_fields.py:47-182 ----
+    const float p0x = fmaf(-pc.c, u, pc.a), p0y = fmaf(-pc.c, v, pc.b);
+    float px = p0x, py = p0y, iota = 0.f;
+    if constexpr (K > 0) {
+      iota = fmaf(u, p0x, v * p0y);
+      const float pi = m.phi * iota;
+      px = fmaf(m.s, p0x, pi * u);
+      py = fmaf(m.s, p0y, pi * v);
+    }
+    const float rho2 = fmaf(px, px, py * py);
+    const float irho = fast_rsqrt(fmaxf(rho2, 1e-24f));  // F.normalize eps (perspective_fields.py:79)
+    const float upx = px * irho, upy = py * irho;
+    const float q = irho * irho;
+    const float Ap = -py * q, Bp = px * q;  // (n_perp . z)/rho = Ap z_x + Bp z_y
+    const float Nu = fmaf(Ap, u, Bp * v);
+    // residual (lm_optimizer.py:266) and its component along n_perp
+    const float rx = ox - upx, ry = oy - upy;
+    e = fmaf(upx, oy, -upy * ox);
+    const float chi = fmaf(rx, rx, ry * ry) * inv_up2;
+    // Huber (lm_optimizer.py:79-87): chi + 1e-8 == chi in fp32 for chi > 1
+    const float mm = fmaxf(chi, 1.f);
+    const float isx = fast_rsqrt(mm);
+    const float cost = fminf(chi, 1.f) * fmaf(2.f * mm, isx, -1.f);
+    w_up = isx * cu;
+    acc[NH + NF] = fmaf(cost, cu, acc[NH + NF]);
+    // gravity columns: M z_j, z_j = (T0j - u T2j, T1j - v T2j)
+    if constexpr (K == 0) {
+      su_[0] = fmaf(Ap, pc.T00, fmaf(Bp, pc.T10, -pc.T20 * Nu));
+      su_[1] = fmaf(Ap, pc.T01, fmaf(Bp, pc.T11, -pc.T21 * Nu));
+    } else {
+      const float z0x = fmaf(-u, pc.T20, pc.T00), z0y = fmaf(-v, pc.T20, pc.T10);
+      const float z1x = fmaf(-u, pc.T21, pc.T01), z1y = fmaf(-v, pc.T21, pc.T11);
+      const float pn = m.phi * Nu;
+      su_[0] = fmaf(m.s, fmaf(Ap, z0x, Bp * z0y), pn * fmaf(u, z0x, v * z0y));
+      su_[1] = fmaf(m.s, fmaf(Ap, z1x, Bp * z1y), pn * fmaf(u, z1x, v * z1y));
+    }
+    // focal column
+    if constexpr (!GEN_D) {
+      if constexpr (K == 0) {
+        su_[2] = pc.c * Nu;
+      } else {
+        const float Np0 = fmaf(Ap, p0x, Bp * p0y);
+        const float t = fmaf(pc.c, fmaf(m.phi, r2, m.s), -iota * (fmaf(m.Bc, r2, m.A) + m.phi));
+        su_[2] = fmaf(Nu, t, -m.phi * r2 * Np0);
+      }
+    } else {
+      const float Nd = fmaf(Ap, dx, Bp * dy);
+      if constexpr (K == 0) {
+        su_[2] = -pc.c * Nd;
+      } else {
+        const float Np0 = fmaf(Ap, p0x, Bp * p0y);
+        const float p0d = fmaf(p0x, dx, p0y * dy);
+        const float t = fmaf(iota * m.Bc, uvd, m.phi * (p0d - pc.c * uvd));
+        su_[2] = fmaf(fmaf(iota, m.A, -pc.c * m.s), Nd, fmaf(m.phi * uvd, Np0, Nu * t));
+      }
+    }
+    if constexpr (K > 0) {
+      const float Np0 = fmaf(Ap, p0x, Bp * p0y);
+      const float iN = iota * Nu;
+#pragma unroll
+      for (int k = 0; k < K; k++) su_[3 + k] = fmaf(m.sk[k], Np0, m.psi[k] * iN);
+    }
+  }
+
+  if (has_lat) {  // ---- latitude field: perspective_fields.py:185-275 ----
+    const float S = fmaf(pc.a, u, pc.b * v);
+    float m2, ln;
+    if constexpr (K == 0) { m2 = r2 + 1.f; ln = S + pc.c; }
+    else { m2 = fmaf(m.su * m.su, r2, 1.f); ln = fmaf(m.su, S, pc.c); }
+    const float im = fast_rsqrt(m2);
+    const float l = ln * im;
+    const float lc = fminf(fmaxf(l, -1.f + 1e-6f), 1.f - 1e-6f);
+    r_lat = sin_olat - lc;  // lm_optimizer.py:270-271
+    const float chi = r_lat * r_lat * inv_lat2;
+    const float mm = fmaxf(chi, 1.f);
+    const float isx = fast_rsqrt(mm);
+    const float cost = fminf(chi, 1.f) * fmaf(2.f * mm, isx, -1.f);
+    w_lat = isx * cl;
+    acc[NH + NF + 1] = fmaf(cost, cl, acc[NH + NF + 1]);
+    if constexpr (K == 0) {
+      sl_[0] = im * fmaf(pc.T00, u, fmaf(pc.T10, v, pc.T20));
+      sl_[1] = im * fmaf(pc.T01, u, fmaf(pc.T11, v, pc.T21));
+    } else {
+      sl_[0] = im * fmaf(m.su, fmaf(pc.T00, u, pc.T10 * v), pc.T20);
+      sl_[1] = im * fmaf(m.su, fmaf(pc.T01, u, pc.T11 * v), pc.T21);
+    }
+    const float li = l * im;
+    if constexpr (!GEN_D) {
+      if constexpr (K == 0) {
+        sl_[2] = im * fmaf(-l, im, pc.c);  // = -gamma.uv with r^2 = m^2 - 1
+      } else {
+        const float guv = im * fmaf(-li * m.su, r2, S);
+        sl_[2] = -fmaf(m.Q, r2, m.su) * guv;
+#pragma unroll
+        for (int k = 0; k < K; k++) sl_[3 + k] = m.om[k] * guv;
+      }
+    } else {
+      const float U = m.su * u, V = m.su * v;
+      const float gx = fmaf(-U, li, pc.a) * im, gy = fmaf(-V, li, pc.b) * im;
+      const float gd = fmaf(gx, dx, gy * dy);
+      const float guv = fmaf(gx, u, gy * v);
+      sl_[2] = fmaf(m.su, gd, m.Q * uvd * guv);
+      if constexpr (K > 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) sl_[3 + k] = m.om[k] * guv;
+      }
+    }
+  }
+
+  // ---- J^T W J, J^T W r (lm_optimizer.py:346-359) ----
+  float wu[NF], wl[NF];
+#pragma unroll
+  for (int i = 0; i < NF; i++) {
+    wu[i] = has_up ? w_up * su_[i] : 0.f;
+    wl[i] = has_lat ? w_lat * sl_[i] : 0.f;
+  }
+  int idx = 0;
+#pragma unroll
+  for (int i = 0; i < NF; i++) {
+#pragma unroll
+    for (int j = i; j < NF; j++) {
+      float h = acc[idx];
+      if (has_up) h = fmaf(wu[i], su_[j], h);
+      if (has_lat) h = fmaf(wl[i], sl_[j], h);
+      acc[idx++] = h;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < NF; i++) {
+    float g = acc[NH + i];
+    if (has_up) g = fmaf(wu[i], e, g);
+    if (has_lat) g = fmaf(wl[i], r_lat, g);
+    acc[NH + i] = g;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// small dense linear algebra (n <= 5), single thread
+// ------------------------------------------------------------------------------------------
+// In-place lower Cholesky; returns false when not positive definite (torch.linalg.cholesky raises,
+// lm_optimizer.py:129-133).
+__device__ inline bool cholesky(float* A, int n) {
+  for (int j = 0; j < n; j++) {
+    float d = A[j * n + j];
+    for (int k = 0; k < j; k++) d -= A[j * n + k] * A[j * n + k];
+    if (!(d > 0.f)) return false;
+    d = sqrtf(d);
+    A[j * n + j] = d;
+    for (int i = j + 1; i < n; i++) {
+      float s = A[i * n + j];
+      for (int k = 0; k < j; k++) s -= A[i * n + k] * A[j * n + k];
+      A[i * n + j] = s / d;
+    }
+  }
+  return true;
+}
+__device__ inline void cholesky_solve(const float* L, int n, float* b) {
+  for (int i = 0; i < n; i++) {
+    float s = b[i];
+    for (int k = 0; k < i; k++) s -= L[i * n + k] * b[k];
+    b[i] = s / L[i * n + i];
+  }
+  for (int i = n - 1; i >= 0; i--) {
+    float s = b[i];
+    for (int k = i + 1; k < n; k++) s -= L[k * n + i] * b[k];
+    b[i] = s / L[i * n + i];
+  }
+}
+// Gauss-Jordan inverse with partial pivoting (torch.inverse, lm_optimizer.py:484).
+__device__ inline bool invert(const float* A, int n, float* Ainv) {
+  float a[MAX_NF][2 * MAX_NF];
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) { a[i][j] = A[i * n + j]; a[i][n + j] = i == j ? 1.f : 0.f; }
+  for (int c = 0; c < n; c++) {
+    int piv = c;
+    for (int r = c + 1; r < n; r++) if (fabsf(a[r][c]) > fabsf(a[piv][c])) piv = r;
+    if (a[piv][c] == 0.f || !isfinite(a[piv][c])) return false;
+    if (piv != c) for (int j = 0; j < 2 * n; j++) { float t = a[c][j]; a[c][j] = a[piv][j]; a[piv][j] = t; }
+    const float inv = 1.f / a[c][c];
+    for (int j = 0; j < 2 * n; j++) a[c][j] *= inv;
+    for (int r = 0; r < n; r++) if (r != c) {
+      const float f = a[r][c];
+      if (f != 0.f) for (int j = 0; j < 2 * n; j++) a[r][j] -= f * a[c][j];
+    }
+  }
+  for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) Ainv[i * n + j] = a[i][n + j];
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------
+// parameter updates: lm_optimizer.py:518-549
+// ------------------------------------------------------------------------------------------
+__device__ inline void gravity_update(float g[3], float d0, float d1, bool spherical) {
+  if (spherical) {  // SphericalManifold.plus, misc.py:233-259
+    const float nx = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
+    const float nd = sqrtf(d0 * d0 + d1 * d1);
+    const float nd_ = nd < 1e-7f ? nd + 1e-7f : nd;
+    const float sinc = nd < 1e-7f ? 1.f : sinf(nd_) / nd_;
+    const float ex[3] = {sinc * d0, sinc * d1, cosf(nd)};
+    float hv[3], beta;
+    householder(g, hv, beta);
+    const float dot = hv[0] * ex[0] + hv[1] * ex[1] + hv[2] * ex[2];
+    for (int i = 0; i < 3; i++) g[i] = nx * (ex[i] - hv[i] * (beta * dot));
+  } else {  // EuclideanManifold on (roll,pitch) then from_rp (gravity.py:29-40,112-119)
+    float roll, pitch;
+    gravity_rp(g, roll, pitch);
+    roll += d0; pitch += d1;
+    float sr, cr, sp, cp;
+    sincosf(roll, &sr, &cr);
+    sincosf(pitch, &sp, &cp);
+    g[0] = -sr * cp; g[1] = -cr * cp; g[2] = sp;
+  }
+  normalize3(g);
+}
+
+__device__ inline void focal_update(float cam[8], float delta, bool as_log) {  // camera.py:136-152
+  const float h = cam[1];
+  float fy = as_log ? expf(logf(cam[3]) + delta) : cam[3] + delta;
+  const float pi = 3.14159265358979323846f;
+  const float min_f = h / 2.f / tanf((150.f / 180.f * pi) / 2.f);  // vfov 150 deg
+  const float max_f = h / 2.f / tanf((5.f / 180.f * pi) / 2.f);    // vfov 5 deg
+  fy = fminf(fmaxf(fy, min_f), max_f);
+  const float fx = fy * cam[2] / cam[3];
+  cam[2] = fx; cam[3] = fy;
+}
+
+__device__ inline void dist_update(int model, float cam[8], const float* d) {
+  // camera.py:599-604,700-705,817-822.  `dist` is _data[6:] (2 wide) for one-parameter models, so
+  // delta k1 is broadcast into the unused k2 slot as well -- kept for bit-level
+  // equality of camera._data.
+  const float lim = model == SIMPLE_DIVISIONAL ? 3.0f : 0.7f;
+  const float d1 = model == RADIAL ? d[1] : d[0];
+  cam[6] = fminf(fmaxf(cam[6] + d[0], -lim), lim);
+  cam[7] = fminf(fmaxf(cam[7] + d1, -lim), lim);
+}
+
+}  // namespace gclm

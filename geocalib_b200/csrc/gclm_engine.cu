@@ -1,0 +1,756 @@
+// gclm_engine.cu -- fused residual + Jacobian + reduce + solve pass for sm_100a and the C ABI.
+//
+// One LM iteration == one launch of lm_pass_kernel over the whole batch:
+//   grid  = B * tiles_per_image CTAs; a tile is `rows_per_tile` image rows of ONE image
+//   warp  = one 128-pixel-wide column strip (32 lanes x float4) walked down the rows, so every
+//           warp-level load is a fully coalesced 512 B segment of each of the 5 planes and the
+//           per-column terms (u, ...) stay in registers for the whole strip
+//   CTA   = warp-shuffle + shared-memory reduction of the NACC accumulators -> one partial per
+//           tile in global scratch -> atomic ticket; the LAST CTA of an image sums the partials in
+//           tile order (deterministic), then one thread runs the damped Cholesky solve, the
+//           manifold update, the lambda schedule and the early-stop bookkeeping and writes the new
+//           parameters for the next launch.  No host round trip anywhere (the reference crosses
+//           the device boundary twice per iteration: lm_optimizer.py:128,137).
+//   pass num_steps (the final one) re-evaluates costs at the final estimate and accumulates the
+//   Hessian in the (roll,pitch,f,k) basis for the covariance (lm_optimizer.py:632-636, 463-516).
+//
+// Passes per solve: num_steps + 1 (the reference makes 2*num_steps + 2 logical passes).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+#include "../../include/gclm.h"
+#include "gclm_device.cuh"
+
+namespace gclm {
+
+// ---------------------------------------------------------------------------------------------
+// device-side state
+// ---------------------------------------------------------------------------------------------
+constexpr int PSTRIDE = 12;  // cam[8] + g[3] + pad
+constexpr unsigned FLAG_FROZEN = 0x100u;
+constexpr int MAX_WARPS = 10;
+
+struct Ctrl {
+  int stop;            // batch-global early stop fired: later LM passes are no-ops
+  int stop_at;         // first iteration (1-based) at which all images were converged
+  unsigned done[2];    // images finished in the current pass (ping-pong by pass parity)
+  unsigned unconv[2];  // images NOT converged in the current pass
+};
+
+struct PassArgs {
+  const float *up, *lat, *uconf, *lconf;
+  int B, H, W;
+  int rows_per_tile, tiles_per_image, rsub;
+  int pass, is_final, shared;
+  int model, num_steps, early_stop, fix_lambda, spherical, log_focal, stop_mode;
+  int est_gravity, est_focal, est_dist, compute_unc;
+  float lambda0, atol, rtol, up_scale, lat_scale;
+  // scratch state
+  float* P;            // (B,2,PSTRIDE) double-buffered parameters
+  float* lam;          // (B)
+  float* prev_cost;    // (B)
+  float* cost0;        // (B,3) initial costs
+  int* slot;           // (B) which P buffer is current
+  unsigned* flags;     // (B) status bits | FLAG_FROZEN
+  int* stop_at;        // (B) per-image mode
+  float* partials;     // (B,S,NACC)
+  unsigned* tickets;   // (B)
+  Ctrl* ctrl;
+  // shared-intrinsics scratch
+  float* schur;        // (B,SCHUR_STRIDE)
+  gclm_result res;
+};
+
+__device__ __forceinline__ float4 ldg_stream(const float* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ int active_columns(int model, int est_gravity, int est_focal, int* act) {
+  int n = 0;  // lm_optimizer.py:335-344
+  if (est_gravity) { act[n++] = 0; act[n++] = 1; }
+  if (est_focal) act[n++] = 2;
+  for (int k = 0; k < num_dist(model); k++) act[n++] = 3 + k;
+  return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-image epilogue, executed by ONE thread of the last CTA of the image
+// ---------------------------------------------------------------------------------------------
+template <int MODEL>
+__device__ __noinline__ void finalize_image(const PassArgs& a, int b, const float* sums, int sl) {
+  constexpr int K = Dims<MODEL>::K, NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH;
+  const float invN = 1.f / ((float)a.H * (float)a.W);
+  const float cu = sums[NH + NF] * (a.up_scale * a.up_scale) * invN;
+  const float cl = sums[NH + NF + 1] * (a.lat_scale * a.lat_scale) * invN;
+  const float* Pb = a.P + ((size_t)b * 2 + sl) * PSTRIDE;
+  unsigned fl = a.flags[b] & 0xffu;
+  int act[NF];
+  const int n = active_columns(MODEL, a.est_gravity, a.est_focal, act);
+  float Hf[NF][NF];
+  {
+    int idx = 0;
+    for (int i = 0; i < NF; i++)
+      for (int j = i; j < NF; j++) { Hf[i][j] = sums[idx]; Hf[j][i] = sums[idx]; idx++; }
+  }
+  float Ha[MAX_NF * MAX_NF];
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j < n; j++) Ha[i * n + j] = Hf[act[i]][act[j]];
+  if (a.res.hessian_rpf)
+    for (int i = 0; i < n * n; i++) a.res.hessian_rpf[(size_t)b * n * n + i] = Ha[i];
+  if (a.compute_unc && (a.res.covariance || a.res.uncertainty)) {
+    float Cv[MAX_NF * MAX_NF];
+    float unc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (!invert(Ha, n, Cv)) {
+      fl |= GCLM_STATUS_COV_SINGULAR;
+      for (int i = 0; i < n * n; i++) Cv[i] = __int_as_float(0x7fc00000);
+    }
+    if (a.est_gravity) {  // lm_optimizer.py:489-499
+      unc[0] = sqrtf(Cv[0]);
+      unc[1] = sqrtf(Cv[n + 1]);
+      const float p = Cv[0], q = Cv[n], r = Cv[n + 1];  // eigvalsh reads the lower triangle
+      const float tr = 0.5f * (p + r), df = 0.5f * (p - r);
+      unc[2] = sqrtf(tr + sqrtf(df * df + q * q));
+    }
+    if (a.est_focal) {  // :501-515, misc.py:284-287
+      const int fi = a.est_gravity ? 2 : 0;
+      const float cff = Cv[fi * n + fi];
+      const float fy = Pb[3], h = Pb[1];
+      const float jf = -4.f * h / (4.f * fy * fy + h * h);
+      unc[3] = sqrtf(cff) / 2.f;
+      unc[4] = sqrtf(jf * jf * cff / 2.f);
+    }
+    if (a.res.covariance)
+      for (int i = 0; i < n * n; i++) a.res.covariance[(size_t)b * n * n + i] = Cv[i];
+    if (a.res.uncertainty)
+      for (int i = 0; i < 5; i++) a.res.uncertainty[(size_t)b * 5 + i] = unc[i];
+  }
+  if (a.res.costs) {
+    float* c = a.res.costs + (size_t)b * 6;
+    if (a.num_steps == 0) { c[0] = cu + cl; c[1] = cu; c[2] = cl; }
+    else { c[0] = a.cost0[b * 3]; c[1] = a.cost0[b * 3 + 1]; c[2] = a.cost0[b * 3 + 2]; }
+    c[3] = cu + cl; c[4] = cu; c[5] = cl;
+  }
+  if (a.res.camera) for (int i = 0; i < 8; i++) a.res.camera[(size_t)b * 8 + i] = Pb[i];
+  if (a.res.gravity) for (int i = 0; i < 3; i++) a.res.gravity[(size_t)b * 3 + i] = Pb[8 + i];
+  if (a.res.stop_at)
+    a.res.stop_at[b] = (a.stop_mode == GCLM_STOP_PER_IMAGE && !a.shared) ? a.stop_at[b] : a.ctrl->stop_at;
+  if (a.res.status) a.res.status[b] = fl;
+  (void)K;
+}
+
+__device__ __forceinline__ bool allclose1(float nw, float prev, float atol, float rtol) {
+  if (nw == prev) return true;  // torch.allclose(new, prev): |new - prev| <= atol + rtol |prev|
+  return fabsf(nw - prev) <= atol + rtol * fabsf(prev);  // NaN -> false
+}
+
+// Batch-global early-stop bookkeeping (lm_optimizer.py:90-92, 619-625): the last image to finish
+// this pass knows whether ALL images were converged.
+__device__ __forceinline__ void batch_stop_vote(const PassArgs& a, bool converged) {
+  Ctrl* c = a.ctrl;
+  const int par = a.pass & 1;
+  if (!converged) atomicAdd(&c->unconv[par], 1u);
+  __threadfence();
+  const unsigned t = atomicAdd(&c->done[par], 1u);
+  if (t == (unsigned)a.B - 1u) {
+    __threadfence();
+    const unsigned un = atomicAdd(&c->unconv[par], 0u);
+    if (un == 0u) {
+      if (a.pass < c->stop_at) c->stop_at = a.pass;  // infos["stop_at"] = min(i + 1, ...)
+      if (a.early_stop) c->stop = 1;
+    }
+    c->done[par ^ 1] = 0u;  // arm the counters of the next pass
+    c->unconv[par ^ 1] = 0u;
+    __threadfence();
+  }
+}
+
+template <int MODEL>
+__device__ __noinline__ void lm_step_image(const PassArgs& a, int b, const float* sums) {
+  constexpr int K = Dims<MODEL>::K, NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH;
+  int sl = a.slot[b];
+  if (a.is_final) {
+    if (a.ctrl->stop) sl ^= 1;  // batch stop fired: the tentative update of that pass is dropped
+    finalize_image<MODEL>(a, b, sums, sl);
+    return;
+  }
+  const float invN = 1.f / ((float)a.H * (float)a.W);
+  const float cu = sums[NH + NF] * (a.up_scale * a.up_scale) * invN;
+  const float cl = sums[NH + NF + 1] * (a.lat_scale * a.lat_scale) * invN;
+  const float cost = cu + cl;  // lm_optimizer.py:584,610
+  float lam = a.lam[b];
+  bool converged = false;
+  if (a.pass == 0) {
+    a.cost0[b * 3] = cost; a.cost0[b * 3 + 1] = cu; a.cost0[b * 3 + 2] = cl;
+  } else {
+    // this pass evaluated cost(theta_i) == "new_cost" of iteration i-1 (lm_optimizer.py:607-613)
+    const float prev = a.prev_cost[b];
+    if (!a.fix_lambda) lam = fminf(fmaxf(lam * (cost > prev ? 10.f : 0.1f), 1e-6f), 1e2f);
+    converged = allclose1(cost, prev, a.atol, a.rtol);
+    if (a.stop_mode == GCLM_STOP_PER_IMAGE && converged) {
+      if (a.pass < a.stop_at[b]) a.stop_at[b] = a.pass;
+      if (a.early_stop) {  // freeze: theta_i is final, no further work on this image
+        a.flags[b] |= FLAG_FROZEN;
+        a.prev_cost[b] = cost;
+        return;
+      }
+    }
+  }
+  a.prev_cost[b] = cost;
+  a.lam[b] = lam;
+
+  // ---- optimizer_step (lm_optimizer.py:109-137) on the active columns ----
+  int act[NF];
+  const int n = active_columns(MODEL, a.est_gravity, a.est_focal, act);
+  float Hf[NF][NF];
+  {
+    int idx = 0;
+    for (int i = 0; i < NF; i++)
+      for (int j = i; j < NF; j++) { Hf[i][j] = sums[idx]; Hf[j][i] = sums[idx]; idx++; }
+  }
+  float A[MAX_NF * MAX_NF], d[MAX_NF];
+  for (int i = 0; i < n; i++) {
+    d[i] = sums[NH + act[i]];
+    for (int j = 0; j < n; j++) A[i * n + j] = Hf[act[i]][act[j]];
+  }
+  for (int i = 0; i < n; i++) A[i * n + i] += fmaxf(A[i * n + i] * lam, 1e-6f);
+  if (cholesky(A, n)) cholesky_solve(A, n, d);
+  else {
+    for (int i = 0; i < n; i++) d[i] = 0.f;
+    a.flags[b] |= GCLM_STATUS_CHOLESKY_FAILED;
+  }
+  // ---- update_estimate (lm_optimizer.py:518-549) into the other parameter buffer ----
+  const float* Pc = a.P + ((size_t)b * 2 + sl) * PSTRIDE;
+  float* Pn = a.P + ((size_t)b * 2 + (sl ^ 1)) * PSTRIDE;
+  float cam[8], g[3];
+  for (int i = 0; i < 8; i++) cam[i] = Pc[i];
+  for (int i = 0; i < 3; i++) g[i] = Pc[8 + i];
+  int o = 0;
+  float d0 = 0.f, d1 = 0.f, df = 0.f;
+  if (a.est_gravity) { d0 = d[0]; d1 = d[1]; o = 2; }
+  gravity_update(g, d0, d1, a.spherical);
+  if (a.est_focal) df = d[o++];
+  focal_update(cam, df, a.log_focal);
+  if (K > 0 && a.est_dist) dist_update(MODEL, cam, d + o);
+  for (int i = 0; i < 8; i++) Pn[i] = cam[i];
+  for (int i = 0; i < 3; i++) Pn[8 + i] = g[i];
+  a.slot[b] = sl ^ 1;
+  if (a.stop_mode == GCLM_STOP_BATCH) {
+    if (a.pass >= 1) batch_stop_vote(a, converged);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the fused pass kernel
+// ---------------------------------------------------------------------------------------------
+template <int MODEL, bool GEN_D, bool FULL>
+__global__ void __launch_bounds__(MAX_WARPS * 32) lm_pass_kernel(const PassArgs a) {
+  constexpr int NACC = Dims<MODEL>::NACC;
+  const int b = blockIdx.x / a.tiles_per_image;
+  const int tile = blockIdx.x - b * a.tiles_per_image;
+  if (!a.is_final) {
+    if (*(volatile int*)&a.ctrl->stop) return;
+    if (a.flags[b] & FLAG_FROZEN) return;
+  }
+  __shared__ PassConst s_pc;
+  __shared__ float s_red[MAX_WARPS][NACC];
+  __shared__ float s_sum[NACC];
+  __shared__ int s_last;
+  if (threadIdx.x == 0) {
+    int sl = a.slot[b];
+    if (a.is_final && a.ctrl->stop) sl ^= 1;
+    const float* Pb = a.P + ((size_t)b * 2 + sl) * PSTRIDE;
+    make_pass_const(Pb, Pb + 8, a.spherical != 0, a.log_focal != 0, a.is_final != 0, s_pc);
+  }
+  __syncthreads();
+  const PassConst pc = s_pc;
+  const FieldMask fm = {a.up != nullptr, a.lat != nullptr, a.uconf != nullptr, a.lconf != nullptr};
+  const float inv_up2 = 1.f / (a.up_scale * a.up_scale), inv_lat2 = 1.f / (a.lat_scale * a.lat_scale);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int W = a.W, H = a.H;
+  const size_t N = (size_t)H * W;
+  const int NS = (W + 127) >> 7;
+  const int yt0 = tile * a.rows_per_tile;
+  const int yt1 = min(H, yt0 + a.rows_per_tile);
+  const int RJ = (a.rows_per_tile + a.rsub - 1) / a.rsub;
+
+  float acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; i++) acc[i] = 0.f;
+
+  for (int job = warp; job < NS * a.rsub; job += nwarps) {
+    const int strip = job % NS, sub = job / NS;
+    const int x0 = (strip << 7) + (lane << 2);
+    const int y0 = yt0 + sub * RJ, y1 = min(yt1, y0 + RJ);
+    if (x0 >= W) continue;  // W % 4 == 0 is enforced on the host
+    float u[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) u[i] = ((float)(x0 + i) - pc.cx) * pc.inv_fx;
+    const size_t off = (size_t)y0 * W + x0;
+    const float* p_ux = (FULL || fm.up) ? a.up + (size_t)b * 2 * N + off : nullptr;
+    const float* p_lat = (FULL || fm.lat) ? a.lat + (size_t)b * N + off : nullptr;
+    const float* p_cu = (FULL || fm.up_conf) ? a.uconf + (size_t)b * N + off : nullptr;
+    const float* p_cl = (FULL || fm.lat_conf) ? a.lconf + (size_t)b * N + off : nullptr;
+#pragma unroll 2
+    for (int y = y0; y < y1; ++y) {
+      float4 ox = make_float4(0.f, 0.f, 0.f, 0.f), oy = ox, ol = ox;
+      float4 cu = make_float4(1.f, 1.f, 1.f, 1.f), cl = cu;
+      if (FULL || fm.up) { ox = ldg_stream(p_ux); oy = ldg_stream(p_ux + N); p_ux += W; }
+      if (FULL || fm.lat) { ol = ldg_stream(p_lat); p_lat += W; }
+      if (FULL || fm.up_conf) { cu = ldg_stream(p_cu); p_cu += W; }
+      if (FULL || fm.lat_conf) { cl = ldg_stream(p_cl); p_cl += W; }
+      const float v = ((float)y - pc.cy) * pc.inv_fy;
+      float sl[4] = {0.f, 0.f, 0.f, 0.f};
+      if (FULL || fm.lat) sin4(ol, sl);
+      pixel_accumulate<MODEL, GEN_D, FULL>(pc, fm, u[0], v, ox.x, oy.x, sl[0], cu.x, cl.x, inv_up2, inv_lat2, acc);
+      pixel_accumulate<MODEL, GEN_D, FULL>(pc, fm, u[1], v, ox.y, oy.y, sl[1], cu.y, cl.y, inv_up2, inv_lat2, acc);
+      pixel_accumulate<MODEL, GEN_D, FULL>(pc, fm, u[2], v, ox.z, oy.z, sl[2], cu.z, cl.z, inv_up2, inv_lat2, acc);
+      pixel_accumulate<MODEL, GEN_D, FULL>(pc, fm, u[3], v, ox.w, oy.w, sl[3], cu.w, cl.w, inv_up2, inv_lat2, acc);
+    }
+  }
+
+  // ---- CTA reduction: shuffle tree, then fixed-order sum over warps ----
+#pragma unroll
+  for (int i = 0; i < NACC; i++) {
+    float x = acc[i];
+    x += __shfl_xor_sync(0xffffffffu, x, 16);
+    x += __shfl_xor_sync(0xffffffffu, x, 8);
+    x += __shfl_xor_sync(0xffffffffu, x, 4);
+    x += __shfl_xor_sync(0xffffffffu, x, 2);
+    x += __shfl_xor_sync(0xffffffffu, x, 1);
+    if (lane == 0) s_red[warp][i] = x;
+  }
+  __syncthreads();
+  const int S = a.tiles_per_image;
+  if (threadIdx.x < NACC) {
+    float s = 0.f;
+    for (int w = 0; w < nwarps; w++) s += s_red[w][threadIdx.x];
+    if (S == 1) s_sum[threadIdx.x] = s;
+    else { a.partials[((size_t)b * S + tile) * NACC + threadIdx.x] = s; __threadfence(); }
+  }
+  __syncthreads();
+  if (S > 1) {
+    if (threadIdx.x == 0) {
+      const unsigned t = atomicAdd(&a.tickets[b], 1u);
+      s_last = (t == (unsigned)S - 1u);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < NACC) {  // deterministic: tile order, independent of arrival order
+      float s = 0.f;
+      const float* p = a.partials + (size_t)b * S * NACC + threadIdx.x;
+      for (int t = 0; t < S; t++) s += __ldcg(p + (size_t)t * NACC);
+      s_sum[threadIdx.x] = s;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    a.tickets[b] = 0u;
+    lm_step_image<MODEL>(a, b, s_sum);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// small kernels
+// ---------------------------------------------------------------------------------------------
+__global__ void lm_init_kernel(PassArgs a, const float* cam0, const float* g0) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) {
+    a.ctrl->stop = 0; a.ctrl->stop_at = a.num_steps;
+    a.ctrl->done[0] = a.ctrl->done[1] = 0u;
+    a.ctrl->unconv[0] = a.ctrl->unconv[1] = 0u;
+  }
+  if (b >= a.B) return;
+  float* P0 = a.P + (size_t)b * 2 * PSTRIDE;
+  for (int i = 0; i < 8; i++) P0[i] = cam0[(size_t)b * 8 + i];
+  float g[3] = {g0[(size_t)b * 3], g0[(size_t)b * 3 + 1], g0[(size_t)b * 3 + 2]};
+  normalize3(g);  // Gravity.__init__ (gravity.py:26)
+  for (int i = 0; i < 3; i++) P0[8 + i] = g[i];
+  for (int i = 0; i < PSTRIDE; i++) P0[PSTRIDE + i] = P0[i];
+  a.lam[b] = a.lambda0;
+  a.prev_cost[b] = 0.f;
+  a.slot[b] = 0;
+  a.flags[b] = 0u;
+  a.stop_at[b] = a.num_steps;
+  a.tickets[b] = 0u;
+}
+
+// counter-based RNG for the synthetic generator (splitmix64 finaliser)
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9e3779b97f4a7c15ull;
+  z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+  z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+  return z ^ (z >> 31);
+}
+__device__ __forceinline__ float u01(uint64_t r) { return ((r >> 40) + 0.5f) * (1.0f / 16777216.0f); }
+__device__ __forceinline__ void normal2(uint64_t r, float& n0, float& n1) {
+  const float a = u01(r), b = u01(r << 24 | (r >> 40));
+  const float rad = sqrtf(-2.f * logf(a));
+  float s, c;
+  sincosf(6.28318530717958647692f * b, &s, &c);
+  n0 = rad * c; n1 = rad * s;
+}
+
+template <int MODEL>
+__global__ void render_kernel(int B, int H, int W, const float* cam, const float* grav, float sigma,
+                              float conf_lo, uint64_t seed, float* up, float* lat, float* uconf,
+                              float* lconf) {
+  const size_t N = (size_t)H * W;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * N) return;
+  const int b = (int)(idx / N);
+  const size_t n = idx - (size_t)b * N;
+  const int y = (int)(n / W), x = (int)(n - (size_t)y * W);
+  const float* c = cam + (size_t)b * 8;
+  float g[3] = {grav[(size_t)b * 3], grav[(size_t)b * 3 + 1], grav[(size_t)b * 3 + 2]};
+  PassConst pc;
+  pc.inv_fx = 1.f / c[2]; pc.inv_fy = 1.f / c[3]; pc.cx = c[4]; pc.cy = c[5];
+  pc.k1 = c[6]; pc.k2 = c[7]; pc.a = g[0]; pc.b = g[1]; pc.c = g[2];
+  const float u = ((float)x - pc.cx) / c[2], v = ((float)y - pc.cy) / c[3];
+  const float r2 = u * u + v * v;
+  ModelScalars<num_dist(MODEL)> m;
+  model_scalars<MODEL>(pc, r2, m);
+  const float p0x = g[0] - g[2] * u, p0y = g[1] - g[2] * v;
+  const float iota = u * p0x + v * p0y;
+  float px = m.s * p0x + m.phi * iota * u, py = m.s * p0y + m.phi * iota * v;
+  const float rho = fmaxf(sqrtf(px * px + py * py), 1e-12f);
+  px /= rho; py /= rho;
+  const float U = m.su * u, V = m.su * v;
+  const float mm = sqrtf(U * U + V * V + 1.f);
+  const float l = (U * g[0] + V * g[1] + g[2]) / mm;
+  float la = asinf(fminf(fmaxf(l, -1.f + 1e-6f), 1.f - 1e-6f));
+  const uint64_t r0 = mix64(seed ^ (idx * 4 + 0)), r1 = mix64(seed ^ (idx * 4 + 1));
+  const uint64_t r2_ = mix64(seed ^ (idx * 4 + 2));
+  if (sigma > 0.f) {
+    float n0, n1, n2, n3;
+    normal2(r0, n0, n1);
+    normal2(r1, n2, n3);
+    px += sigma * n0; py += sigma * n1; la += sigma * n2;
+    const float nr = fmaxf(sqrtf(px * px + py * py), 1e-12f);
+    px /= nr; py /= nr;
+  }
+  if (up) { up[(size_t)b * 2 * N + n] = px; up[(size_t)b * 2 * N + N + n] = py; }
+  if (lat) lat[(size_t)b * N + n] = la;
+  if (uconf) uconf[(size_t)b * N + n] = conf_lo + (1.f - conf_lo) * u01(r2_);
+  if (lconf) lconf[(size_t)b * N + n] = conf_lo + (1.f - conf_lo) * u01(r2_ << 24 | (r2_ >> 40));
+}
+
+}  // namespace gclm
+
+// =============================================================================================
+// host side
+// =============================================================================================
+using namespace gclm;
+
+struct gclm_handle {
+  int device = 0;
+  int num_sms = 148;
+  int64_t launches = 0;
+  // scratch
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  // host-path staging
+  void* stage[2] = {nullptr, nullptr};
+  size_t stage_bytes = 0;
+  cudaStream_t hstream[2] = {nullptr, nullptr};
+  cudaEvent_t hevent[2] = {nullptr, nullptr};
+  char last_error[256] = {0};
+};
+
+struct gclm_comm {
+  void* nccl_lib = nullptr;
+  void* comm = nullptr;
+  int world = 1, rank = 0;
+};
+
+#define CUDA_TRY(h, expr)                                                                  \
+  do {                                                                                     \
+    cudaError_t e_ = (expr);                                                               \
+    if (e_ != cudaSuccess) {                                                               \
+      if (h) snprintf((h)->last_error, sizeof((h)->last_error), "%s: %s", #expr, cudaGetErrorString(e_)); \
+      return e_ == cudaErrorMemoryAllocation ? GCLM_ERR_OUT_OF_MEMORY : GCLM_ERR_CUDA;    \
+    }                                                                                      \
+  } while (0)
+
+namespace {
+
+struct Layout {  // carve the scratch buffer
+  size_t P, lam, prev, cost0, slot, flags, stop_at, tickets, ctrl, partials, schur, total;
+};
+
+constexpr int SCHUR_STRIDE = 48;
+
+struct TileCfg { int nwarps, rsub, rows_per_tile, tiles_per_image; };
+
+TileCfg tile_config(int B, int H, int W, int num_sms, int rows_override) {
+  TileCfg t;
+  const int NS = (W + 127) / 128;
+  if (NS <= MAX_WARPS) { t.rsub = std::max(1, MAX_WARPS / NS); t.nwarps = NS * t.rsub; }
+  else { t.rsub = 1; t.nwarps = 8; }
+  int rj = 48;  // rows walked by one warp per tile
+  if (rows_override > 0) rj = std::max(1, rows_override / t.rsub);
+  else
+    while (rj > 4 && (int64_t)B * ((H + rj * t.rsub - 1) / (rj * t.rsub)) < 12ll * num_sms) rj /= 2;
+  t.rows_per_tile = rj * t.rsub;
+  t.tiles_per_image = (H + t.rows_per_tile - 1) / t.rows_per_tile;
+  return t;
+}
+
+Layout make_layout(int B, int max_tiles) {
+  Layout L;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~size_t(255); return r; };
+  L.P = take(sizeof(float) * (size_t)B * 2 * PSTRIDE);
+  L.lam = take(sizeof(float) * B);
+  L.prev = take(sizeof(float) * B);
+  L.cost0 = take(sizeof(float) * (size_t)B * 3);
+  L.slot = take(sizeof(int) * B);
+  L.flags = take(sizeof(unsigned) * B);
+  L.stop_at = take(sizeof(int) * B);
+  L.tickets = take(sizeof(unsigned) * B);
+  L.ctrl = take(sizeof(Ctrl));
+  L.partials = take(sizeof(float) * (size_t)B * max_tiles * MAX_NACC);
+  L.schur = take(sizeof(float) * (size_t)B * SCHUR_STRIDE + 4096);
+  L.total = o;
+  return L;
+}
+
+int ensure_scratch(gclm_handle* h, size_t bytes) {
+  if (bytes <= h->scratch_bytes) return GCLM_OK;
+  if (h->scratch) cudaFree(h->scratch);
+  h->scratch = nullptr; h->scratch_bytes = 0;
+  CUDA_TRY(h, cudaMalloc(&h->scratch, bytes));
+  h->scratch_bytes = bytes;
+  return GCLM_OK;
+}
+
+int max_tiles_for(int H, int W) {
+  const int NS = (W + 127) / 128;
+  const int rsub = NS <= MAX_WARPS ? std::max(1, MAX_WARPS / NS) : 1;
+  return (H + 4 * rsub - 1) / (4 * rsub) + 1;  // smallest auto tile is 4 rows per warp
+}
+
+template <int MODEL>
+void launch_pass_model(const PassArgs& a, bool gen_d, bool full, dim3 grid, dim3 block, cudaStream_t s) {
+  if (gen_d) {
+    if (full) lm_pass_kernel<MODEL, true, true><<<grid, block, 0, s>>>(a);
+    else lm_pass_kernel<MODEL, true, false><<<grid, block, 0, s>>>(a);
+  } else {
+    if (full) lm_pass_kernel<MODEL, false, true><<<grid, block, 0, s>>>(a);
+    else lm_pass_kernel<MODEL, false, false><<<grid, block, 0, s>>>(a);
+  }
+}
+
+void launch_pass(const PassArgs& a, bool gen_d, bool full, dim3 grid, dim3 block, cudaStream_t s) {
+  switch (a.model) {
+    case PINHOLE: launch_pass_model<PINHOLE>(a, gen_d, full, grid, block, s); break;
+    case SIMPLE_RADIAL: launch_pass_model<SIMPLE_RADIAL>(a, gen_d, full, grid, block, s); break;
+    case RADIAL: launch_pass_model<RADIAL>(a, gen_d, full, grid, block, s); break;
+    default: launch_pass_model<SIMPLE_DIVISIONAL>(a, gen_d, full, grid, block, s); break;
+  }
+}
+
+int validate(const gclm_problem* p, const gclm_options* o) {
+  if (!p || !o) return GCLM_ERR_INVALID_ARGUMENT;
+  if (p->batch <= 0 || p->height <= 0 || p->width <= 0) return GCLM_ERR_INVALID_ARGUMENT;
+  if (p->camera_model < 0 || p->camera_model > 3) return GCLM_ERR_INVALID_ARGUMENT;  // :179-181
+  if (!p->up_field && !p->latitude_field) return GCLM_ERR_INVALID_ARGUMENT;
+  if (!p->camera_init || !p->gravity_init) return GCLM_ERR_INVALID_ARGUMENT;
+  if (p->width % 4 != 0) return GCLM_ERR_UNSUPPORTED;  // float4 rows (the CNN emits /32 sizes)
+  if (o->num_steps < 0 || o->num_steps > 10000) return GCLM_ERR_INVALID_ARGUMENT;
+  if (gclm_num_params(p->camera_model, p->estimate_gravity, p->estimate_focal) <= 0)
+    return GCLM_ERR_INVALID_ARGUMENT;  // "No parameters to optimize" (:342)
+  auto mis = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) != 0; };
+  if (mis(p->up_field) || mis(p->latitude_field) || mis(p->up_confidence) || mis(p->latitude_confidence))
+    return GCLM_ERR_UNSUPPORTED;
+  if (((size_t)p->height * p->width) % 4 != 0) return GCLM_ERR_UNSUPPORTED;
+  return GCLM_OK;
+}
+
+PassArgs make_args(gclm_handle* h, const gclm_problem* p, const gclm_options* o, const gclm_result* r,
+                   const TileCfg& t, const Layout& L) {
+  PassArgs a;
+  memset(&a, 0, sizeof(a));
+  a.up = p->up_field; a.lat = p->latitude_field;
+  a.uconf = p->up_field ? p->up_confidence : nullptr;
+  a.lconf = p->latitude_field ? p->latitude_confidence : nullptr;
+  a.B = p->batch; a.H = p->height; a.W = p->width;
+  a.rows_per_tile = t.rows_per_tile; a.tiles_per_image = t.tiles_per_image; a.rsub = t.rsub;
+  a.model = p->camera_model; a.num_steps = o->num_steps; a.early_stop = o->early_stop;
+  a.fix_lambda = o->fix_lambda; a.spherical = o->use_spherical_manifold; a.log_focal = o->use_log_focal;
+  a.stop_mode = o->stop_mode; a.est_gravity = p->estimate_gravity != 0; a.est_focal = p->estimate_focal != 0;
+  a.est_dist = p->estimate_dist != 0; a.compute_unc = o->compute_uncertainty;
+  a.lambda0 = o->lambda_; a.atol = o->atol; a.rtol = o->rtol;
+  a.up_scale = o->up_loss_fn_scale; a.lat_scale = o->lat_loss_fn_scale;
+  char* base = static_cast<char*>(h->scratch);
+  a.P = reinterpret_cast<float*>(base + L.P);
+  a.lam = reinterpret_cast<float*>(base + L.lam);
+  a.prev_cost = reinterpret_cast<float*>(base + L.prev);
+  a.cost0 = reinterpret_cast<float*>(base + L.cost0);
+  a.slot = reinterpret_cast<int*>(base + L.slot);
+  a.flags = reinterpret_cast<unsigned*>(base + L.flags);
+  a.stop_at = reinterpret_cast<int*>(base + L.stop_at);
+  a.tickets = reinterpret_cast<unsigned*>(base + L.tickets);
+  a.ctrl = reinterpret_cast<Ctrl*>(base + L.ctrl);
+  a.partials = reinterpret_cast<float*>(base + L.partials);
+  a.schur = reinterpret_cast<float*>(base + L.schur);
+  a.res = *r;
+  return a;
+}
+
+}  // namespace
+
+extern "C" {
+
+int gclm_version(void) { return GCLM_VERSION; }
+
+const char* gclm_strerror(int status) {
+  switch (status) {
+    case GCLM_OK: return "ok";
+    case GCLM_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case GCLM_ERR_CUDA: return "CUDA runtime error";
+    case GCLM_ERR_OUT_OF_MEMORY: return "out of device memory";
+    case GCLM_ERR_UNSUPPORTED: return "unsupported configuration (width must be a multiple of 4, 16-byte aligned planes)";
+    case GCLM_ERR_NCCL: return "NCCL error";
+    case GCLM_ERR_NO_DEVICE: return "no CUDA device";
+    default: return "unknown status";
+  }
+}
+
+void gclm_default_options(gclm_options* o) {  // lm_optimizer.py:144-162
+  if (!o) return;
+  memset(o, 0, sizeof(*o));
+  o->num_steps = 30; o->lambda_ = 0.1f; o->fix_lambda = 0; o->early_stop = 1;
+  o->atol = 1e-8f; o->rtol = 1e-8f; o->use_spherical_manifold = 1; o->use_log_focal = 1;
+  o->up_loss_fn_scale = 1e-2f; o->lat_loss_fn_scale = 1e-2f;
+  o->stop_mode = GCLM_STOP_BATCH; o->compute_uncertainty = 1; o->rows_per_tile = 0;
+}
+
+int gclm_num_params(int camera_model, int estimate_gravity, int estimate_focal) {
+  if (camera_model < 0 || camera_model > 3) return GCLM_ERR_INVALID_ARGUMENT;
+  return 2 * (estimate_gravity != 0) + (estimate_focal != 0) + num_dist(camera_model);
+}
+
+int gclm_create(int device, gclm_handle** out) {
+  if (!out) return GCLM_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return GCLM_ERR_NO_DEVICE;
+  if (device < 0 || device >= count) return GCLM_ERR_INVALID_ARGUMENT;
+  gclm_handle* h = new (std::nothrow) gclm_handle();
+  if (!h) return GCLM_ERR_OUT_OF_MEMORY;
+  h->device = device;
+  CUDA_TRY(h, cudaSetDevice(device));
+  int sms = 0;
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
+    h->num_sms = sms;
+  *out = h;
+  return GCLM_OK;
+}
+
+int gclm_destroy(gclm_handle* h) {
+  if (!h) return GCLM_OK;
+  cudaSetDevice(h->device);
+  if (h->scratch) cudaFree(h->scratch);
+  for (int i = 0; i < 2; i++) {
+    if (h->stage[i]) cudaFree(h->stage[i]);
+    if (h->hstream[i]) cudaStreamDestroy(h->hstream[i]);
+    if (h->hevent[i]) cudaEventDestroy(h->hevent[i]);
+  }
+  delete h;
+  return GCLM_OK;
+}
+
+int gclm_reserve(gclm_handle* h, int batch, int height, int width) {
+  if (!h || batch <= 0 || height <= 0 || width <= 0) return GCLM_ERR_INVALID_ARGUMENT;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const Layout L = make_layout(batch, max_tiles_for(height, width));
+  return ensure_scratch(h, L.total);
+}
+
+int64_t gclm_launch_count(const gclm_handle* h) { return h ? h->launches : 0; }
+
+int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt,
+               const gclm_result* res, void* cuda_stream) {
+  if (!h || !res) return GCLM_ERR_INVALID_ARGUMENT;
+  int st = validate(prob, opt);
+  if (st != GCLM_OK) return st;
+  if (prob->shared_intrinsics) return GCLM_ERR_INVALID_ARGUMENT;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  const TileCfg t = tile_config(prob->batch, prob->height, prob->width, h->num_sms, opt->rows_per_tile);
+  const Layout L = make_layout(prob->batch, std::max(t.tiles_per_image, max_tiles_for(prob->height, prob->width)));
+  st = ensure_scratch(h, L.total);
+  if (st != GCLM_OK) return st;
+  PassArgs a = make_args(h, prob, opt, res, t, L);
+  const bool full = a.up && a.lat && a.uconf && a.lconf;
+  lm_init_kernel<<<(prob->batch + 127) / 128, 128, 0, s>>>(a, prob->camera_init, prob->gravity_init);
+  h->launches++;
+  const dim3 grid((unsigned)((size_t)prob->batch * t.tiles_per_image)), block(t.nwarps * 32);
+  for (int it = 0; it < opt->num_steps; it++) {
+    a.pass = it; a.is_final = 0;
+    launch_pass(a, !opt->use_log_focal, full, grid, block, s);
+    h->launches++;
+  }
+  a.pass = opt->num_steps; a.is_final = 1;
+  launch_pass(a, true, full, grid, block, s);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GCLM_OK;
+}
+
+int gclm_solve_shared(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt,
+                      const gclm_result* res, gclm_comm* comm, void* cuda_stream) {
+  (void)h; (void)prob; (void)opt; (void)res; (void)comm; (void)cuda_stream;
+  return GCLM_ERR_UNSUPPORTED;
+}
+
+int gclm_comm_unique_id(void* id_out) { (void)id_out; return GCLM_ERR_UNSUPPORTED; }
+int gclm_comm_create(const void* unique_id, int world_size, int rank, int device, gclm_comm** out) {
+  (void)unique_id; (void)world_size; (void)rank; (void)device; (void)out;
+  return GCLM_ERR_UNSUPPORTED;
+}
+int gclm_comm_destroy(gclm_comm* c) { (void)c; return GCLM_OK; }
+
+int gclm_solve_host(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt,
+                    const gclm_result* res, int chunk_images) {
+  (void)h; (void)prob; (void)opt; (void)res; (void)chunk_images;
+  return GCLM_ERR_UNSUPPORTED;
+}
+
+int gclm_render_fields(gclm_handle* h, int batch, int height, int width, int camera_model,
+                       const float* camera, const float* gravity, float sigma, float conf_lo,
+                       uint64_t seed, float* up_field, float* latitude_field, float* up_confidence,
+                       float* latitude_confidence, void* cuda_stream) {
+  if (!h || batch <= 0 || height <= 0 || width <= 0 || !camera || !gravity) return GCLM_ERR_INVALID_ARGUMENT;
+  if (camera_model < 0 || camera_model > 3) return GCLM_ERR_INVALID_ARGUMENT;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  const size_t total = (size_t)batch * height * width;
+  const unsigned blocks = (unsigned)((total + 255) / 256);
+#define RENDER(M) render_kernel<M><<<blocks, 256, 0, s>>>(batch, height, width, camera, gravity, sigma, conf_lo, seed, up_field, latitude_field, up_confidence, latitude_confidence)
+  switch (camera_model) {
+    case PINHOLE: RENDER(PINHOLE); break;
+    case SIMPLE_RADIAL: RENDER(SIMPLE_RADIAL); break;
+    case RADIAL: RENDER(RADIAL); break;
+    default: RENDER(SIMPLE_DIVISIONAL); break;
+  }
+#undef RENDER
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GCLM_OK;
+}
+
+}  // extern "C"

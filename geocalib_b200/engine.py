@@ -1,0 +1,159 @@
+"""Thin Python handle over the C ABI: device tensors in, device tensors out.
+
+torch is used for device memory and streams only; all arithmetic on the fields happens inside
+libgclm.so.  Inputs must already be CUDA float32 tensors -- there is no CPU path.
+"""
+
+from __future__ import annotations
+
+import ctypes
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import CAMERA_MODEL_IDS, Options, Problem, Result
+
+NUM_DIST = {"pinhole": 0, "simple_radial": 1, "radial": 2, "simple_divisional": 1}
+
+_engines: Dict[int, "Engine"] = {}
+
+
+def get_engine(device: Optional[torch.device] = None) -> "Engine":
+    """One engine (scratch allocator) per CUDA device, created on first use."""
+    if not torch.cuda.is_available():
+        raise _lib.GclmError("geocalib_b200 needs a CUDA device (sm_100a); none is visible")
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    if idx not in _engines:
+        _engines[idx] = Engine(idx)
+    return _engines[idx]
+
+
+def _dev_ptr(t: Optional[torch.Tensor], shape, name: str, device) -> Optional[int]:
+    if t is None:
+        return None
+    if not t.is_cuda or t.device != device:
+        raise _lib.GclmError(f"{name} must live on {device} (got {t.device}); there is no CPU path")
+    if t.dtype != torch.float32:
+        raise _lib.GclmError(f"{name} must be float32 (got {t.dtype})")
+    if tuple(t.shape) != tuple(shape):
+        raise _lib.GclmError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+    if not t.is_contiguous():
+        raise _lib.GclmError(f"{name} must be contiguous")
+    return t.data_ptr()
+
+
+class Engine:
+    """Owns a gclm_handle on one device."""
+
+    def __init__(self, device_index: int):
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device_index)
+        h = ctypes.c_void_p()
+        _lib.check(self.lib.gclm_create(device_index, ctypes.byref(h)), "gclm_create")
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                self.lib.gclm_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.gclm_launch_count(self._h))
+
+    def reserve(self, batch: int, height: int, width: int) -> None:
+        _lib.check(self.lib.gclm_reserve(self._h, batch, height, width), "gclm_reserve")
+
+    # ------------------------------------------------------------------------------------------
+    def solve(
+        self,
+        camera_model: str,
+        up_field: Optional[torch.Tensor],
+        latitude_field: Optional[torch.Tensor],
+        up_confidence: Optional[torch.Tensor],
+        latitude_confidence: Optional[torch.Tensor],
+        camera_init: torch.Tensor,
+        gravity_init: torch.Tensor,
+        *,
+        options: Optional[Options] = None,
+        estimate_gravity: bool = True,
+        estimate_focal: bool = True,
+        estimate_dist: bool = True,
+        shared_intrinsics: bool = False,
+        comm=None,
+        out: Optional[Dict[str, torch.Tensor]] = None,
+    ) -> Dict[str, torch.Tensor]:
+        """Enqueue one batched LM solve on the current stream; returns raw result tensors."""
+        ref = up_field if up_field is not None else latitude_field
+        if ref is None:
+            raise _lib.GclmError("need at least one of up_field / latitude_field")
+        dev = ref.device
+        B, _, H, W = ref.shape
+        opt = options if options is not None else _lib.default_options()
+        n = 2 * int(estimate_gravity) + int(estimate_focal) + NUM_DIST[camera_model]
+        prob = Problem(
+            batch=B, height=H, width=W, camera_model=CAMERA_MODEL_IDS[camera_model],
+            up_field=_dev_ptr(up_field, (B, 2, H, W), "up_field", dev),
+            latitude_field=_dev_ptr(latitude_field, (B, 1, H, W), "latitude_field", dev),
+            up_confidence=_dev_ptr(up_confidence, (B, H, W), "up_confidence", dev),
+            latitude_confidence=_dev_ptr(latitude_confidence, (B, H, W), "latitude_confidence", dev),
+            camera_init=_dev_ptr(camera_init, (B, 8), "camera_init", dev),
+            gravity_init=_dev_ptr(gravity_init, (B, 3), "gravity_init", dev),
+            estimate_gravity=int(estimate_gravity), estimate_focal=int(estimate_focal),
+            estimate_dist=int(estimate_dist), shared_intrinsics=int(shared_intrinsics),
+        )
+        if out is None:
+            f32 = dict(device=dev, dtype=torch.float32)
+            out = {
+                "camera": torch.empty((B, 8), **f32),
+                "gravity": torch.empty((B, 3), **f32),
+                "covariance": torch.zeros((B, n, n), **f32),
+                "uncertainty": torch.zeros((B, 5), **f32),
+                "costs": torch.empty((B, 6), **f32),
+                "stop_at": torch.empty((B,), device=dev, dtype=torch.int32),
+                "status": torch.empty((B,), device=dev, dtype=torch.int32),
+                "hessian_rpf": torch.empty((B, n, n), **f32),
+            }
+        res = Result(**{k: out[k].data_ptr() for k in
+                        ("camera", "gravity", "covariance", "uncertainty", "costs", "stop_at", "status", "hessian_rpf")})
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        with torch.cuda.device(dev):
+            if shared_intrinsics:
+                st = self.lib.gclm_solve_shared(self._h, ctypes.byref(prob), ctypes.byref(opt),
+                                                ctypes.byref(res), comm, stream)
+                _lib.check(st, "gclm_solve_shared")
+            else:
+                st = self.lib.gclm_solve(self._h, ctypes.byref(prob), ctypes.byref(opt),
+                                         ctypes.byref(res), stream)
+                _lib.check(st, "gclm_solve")
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def render_fields(self, camera_model: str, camera: torch.Tensor, gravity: torch.Tensor,
+                      height: int, width: int, *, sigma: float = 0.0, conf_lo: float = 1.0,
+                      seed: int = 0, with_confidence: bool = True) -> Dict[str, torch.Tensor]:
+        """Synthetic predicted fields on device (bench / tests): GT render + noise + confidences."""
+        dev = camera.device
+        B = camera.shape[0]
+        f32 = dict(device=dev, dtype=torch.float32)
+        up = torch.empty((B, 2, height, width), **f32)
+        lat = torch.empty((B, 1, height, width), **f32)
+        uc = torch.empty((B, height, width), **f32) if with_confidence else None
+        lc = torch.empty((B, height, width), **f32) if with_confidence else None
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        st = self.lib.gclm_render_fields(
+            self._h, B, height, width, CAMERA_MODEL_IDS[camera_model],
+            _dev_ptr(camera.contiguous(), (B, 8), "camera", dev),
+            _dev_ptr(gravity.contiguous(), (B, 3), "gravity", dev),
+            float(sigma), float(conf_lo), int(seed) & (2**64 - 1), up.data_ptr(), lat.data_ptr(),
+            uc.data_ptr() if uc is not None else None, lc.data_ptr() if lc is not None else None, stream)
+        _lib.check(st, "gclm_render_fields")
+        out = {"up_field": up, "latitude_field": lat}
+        if with_confidence:
+            out |= {"up_confidence": uc, "latitude_confidence": lc}
+        return out

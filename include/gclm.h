@@ -1,0 +1,199 @@
+/*
+ * gclm.h -- C ABI of the B200-native Levenberg-Marquardt calibration engine (libgclm.so).
+ *
+ * The reference (cvg/GeoCalib @ 3ee7ec34) has NO native boundary for this path: the seam is the
+ * Python object `geocalib.lm_optimizer.LMOptimizer` owned by `geocalib.geocalib.GeoCalib`
+ * (geocalib/geocalib.py:106) and called at geocalib/geocalib.py:119.  This header is therefore the
+ * boundary a maintainer would bind (ctypes stub in INTEGRATION.md); every entry point names the
+ * reference interface it replaces.
+ *
+ * Conventions
+ *   - C linkage, plain pointers and sizes, no C++/torch types, no exceptions across the boundary.
+ *   - Every function returns a gclm_status (0 = ok, <0 = error); gclm_strerror() explains it.
+ *   - All `const float*` inputs and all outputs are DEVICE pointers owned by the caller unless the
+ *     function name ends in `_host`.  The handle owns only scratch memory.
+ *   - Work is enqueued on the caller's CUDA stream (a `cudaStream_t` passed as void*); the library
+ *     never synchronises the device in gclm_solve / gclm_solve_shared.
+ *   - One handle per device; a handle is not thread-safe, different handles are independent.
+ *   - Numerical failure never raises (reference: lm_optimizer.py:129-133, 497-499): a failed
+ *     Cholesky gives a zero step for THAT image and sets bit 0 of its status word.
+ */
+#ifndef GCLM_H_
+#define GCLM_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCLM_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+  GCLM_OK = 0,
+  GCLM_ERR_INVALID_ARGUMENT = -1,
+  GCLM_ERR_CUDA = -2,
+  GCLM_ERR_OUT_OF_MEMORY = -3,
+  GCLM_ERR_UNSUPPORTED = -4,
+  GCLM_ERR_NCCL = -5,
+  GCLM_ERR_NO_DEVICE = -6
+} gclm_status;
+
+/* Camera models: geocalib/camera.py:945-950 (`camera_models`). */
+typedef enum {
+  GCLM_PINHOLE = 0,           /* camera.py:522-562 */
+  GCLM_SIMPLE_RADIAL = 1,     /* camera.py:565-660 */
+  GCLM_RADIAL = 2,            /* camera.py:663-786 */
+  GCLM_SIMPLE_DIVISIONAL = 3  /* camera.py:789-942 */
+} gclm_camera_model;
+
+/* Early-stop semantics (lm_optimizer.py:90-92, 619-625). */
+typedef enum {
+  GCLM_STOP_BATCH = 0,    /* reference: stop when ALL images satisfy allclose() at the same step */
+  GCLM_STOP_PER_IMAGE = 1 /* freeze each image individually as soon as it converged           */
+} gclm_stop_mode;
+
+/* status bits written to gclm_result.status */
+#define GCLM_STATUS_CHOLESKY_FAILED 1u /* lm_optimizer.py:129-133 (per image here) */
+#define GCLM_STATUS_COV_SINGULAR 2u    /* torch.inverse would have raised (lm_optimizer.py:484) */
+#define GCLM_STATUS_NONFINITE 4u
+
+typedef struct gclm_handle gclm_handle;
+
+/*
+ * The optimisation problem: replaces the `data` dict + the LMOptimizer attributes
+ * (lm_optimizer.py:144-171, 189-246, 646-664).
+ */
+typedef struct {
+  int32_t batch;  /* B */
+  int32_t height; /* H of the fields */
+  int32_t width;  /* W of the fields */
+  int32_t camera_model; /* gclm_camera_model; LMOptimizer.set_camera_model (:173-187) */
+
+  /* data["up_field"] (B,2,H,W), data["latitude_field"] (B,1,H,W) radians, contiguous NCHW fp32.
+   * Either may be NULL (lm_optimizer.py:265,269), not both. */
+  const float* up_field;
+  const float* latitude_field;
+  /* data["up_confidence"], data["latitude_confidence"] (B,H,W) or NULL (:295,307). */
+  const float* up_confidence;
+  const float* latitude_confidence;
+
+  /* Initial estimate = get_trivial_estimation() incl. priors/scales (lm_optimizer.py:20-58).
+   * camera_init (B,8) = [w,h,fx,fy,cx,cy,k1,k2] (camera.py:24-41); gravity_init (B,3) unit. */
+  const float* camera_init;
+  const float* gravity_init;
+
+  /* setup_optimization_and_priors (:189-246): which blocks are free. */
+  int32_t estimate_gravity; /* 0 when data has "prior_gravity" */
+  int32_t estimate_focal;   /* 0 when data has "prior_focal"   */
+  int32_t estimate_dist;    /* 0 when data has "prior_dist" (k columns are still solved, :340) */
+  int32_t shared_intrinsics; /* must be 0 for gclm_solve, 1 for gclm_solve_shared */
+} gclm_problem;
+
+/* LMOptimizer.default_conf (lm_optimizer.py:144-162); gclm_default_options() fills the defaults. */
+typedef struct {
+  int32_t num_steps;              /* 30   */
+  float lambda_;                  /* 0.1  */
+  int32_t fix_lambda;             /* 0    */
+  int32_t early_stop;             /* 1    */
+  float atol;                     /* 1e-8 */
+  float rtol;                     /* 1e-8 */
+  int32_t use_spherical_manifold; /* 1    */
+  int32_t use_log_focal;          /* 1    */
+  float up_loss_fn_scale;         /* 1e-2 */
+  float lat_loss_fn_scale;        /* 1e-2 */
+  int32_t stop_mode;              /* gclm_stop_mode; GCLM_STOP_BATCH */
+  int32_t compute_uncertainty;    /* 1 = estimate_uncertainty() (:463-516), eval mode */
+  int32_t rows_per_tile;          /* 0 = auto; tuning knob: image rows per CTA */
+  int32_t reserved[3];
+} gclm_options;
+
+/*
+ * Outputs: replaces the dict returned by LMOptimizer.forward (:509-516, 575-588, 638-644, 664).
+ * All device pointers, caller allocated; any may be NULL to skip that output.
+ * n = 2*estimate_gravity + estimate_focal + num_dist(camera_model) (:421-425).
+ */
+typedef struct {
+  float* camera;      /* (B,8)  out["camera"]._data                                        */
+  float* gravity;     /* (B,3)  out["gravity"].vec3d                                       */
+  float* covariance;  /* (B,n,n) out["covariance"]                                         */
+  float* uncertainty; /* (B,5)  roll, pitch, gravity, focal, vfov _uncertainty              */
+  float* costs;       /* (B,6)  initial_cost, initial_up_cost, initial_latitude_cost,
+                                final_cost, final_up_cost, final_latitude_cost             */
+  int32_t* stop_at;   /* (B)    out["stop_at"]                                             */
+  uint32_t* status;   /* (B)    GCLM_STATUS_* bits                                         */
+  float* hessian_rpf; /* (B,n,n) undamped J^T W J in the (roll,pitch,f,k) basis (:481-483) */
+} gclm_result;
+
+/* Library / build info. */
+int gclm_version(void);
+const char* gclm_strerror(int status);
+void gclm_default_options(gclm_options* opt);
+/* n as defined above, or <0 on invalid model. */
+int gclm_num_params(int camera_model, int estimate_gravity, int estimate_focal);
+
+/* Create / destroy the per-device engine (scratch allocator, SM count query). */
+int gclm_create(int device, gclm_handle** out);
+int gclm_destroy(gclm_handle* h);
+/* Pre-allocate scratch for problems up to (batch,height,width); makes gclm_solve allocation-free
+ * (required before capturing gclm_solve into a CUDA graph). */
+int gclm_reserve(gclm_handle* h, int batch, int height, int width);
+
+/*
+ * Per-image intrinsics: replaces LMOptimizer.forward -> optimize() with shared_intrinsics=False
+ * (lm_optimizer.py:551-644).  Enqueues num_steps+1 fused passes on `cuda_stream`; asynchronous.
+ */
+int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt,
+               const gclm_result* res, void* cuda_stream);
+
+/*
+ * Shared intrinsics: replaces optimize() with shared_intrinsics=True (lm_optimizer.py:350-383,
+ * 599-603): one focal / distortion for the whole batch, per-image gravity.  The dense
+ * (2B+n_i)^2 arrow system of the reference is solved through its Schur complement.
+ * `comm` is NULL for a single GPU, else a handle from gclm_comm_create: the batch is then the
+ * union of all ranks' batches and one all-reduce of <= 2 n_i^2 + 2 n_i + 2 floats is issued per
+ * LM step on `cuda_stream`.
+ */
+typedef struct gclm_comm gclm_comm;
+int gclm_solve_shared(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt,
+                      const gclm_result* res, gclm_comm* comm, void* cuda_stream);
+
+/*
+ * Multi-GPU communicator for gclm_solve_shared (one process per GPU, NCCL over NVLink).
+ * unique_id is GCLM_COMM_ID_BYTES bytes produced on rank 0 by gclm_comm_unique_id and broadcast
+ * by the host framework (torch.distributed in the Python binding).
+ */
+#define GCLM_COMM_ID_BYTES 128
+int gclm_comm_unique_id(void* id_out);
+int gclm_comm_create(const void* unique_id, int world_size, int rank, int device, gclm_comm** out);
+int gclm_comm_destroy(gclm_comm* c);
+
+/*
+ * Host-buffer convenience path (end-to-end measurement; the call a non-CUDA host makes):
+ * all pointers in `prob` and `res` are HOST pointers (pinned for full overlap).  The batch is
+ * processed in chunks of `chunk_images`; H2D copies of chunk k+1 overlap the solve of chunk k on
+ * two internal streams; results are copied back.  Synchronous: returns when `res` is complete.
+ * Per-image intrinsics only; GCLM_STOP_BATCH applies per chunk.
+ */
+int gclm_solve_host(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt,
+                    const gclm_result* res, int chunk_images);
+
+/* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
+int64_t gclm_launch_count(const gclm_handle* h);
+
+/*
+ * Synthetic-field generator used by the benchmark: renders the perspective field of
+ * the given cameras/gravities on device (get_perspective_field, perspective_fields.py:278-320),
+ * adds N(0, sigma^2) noise, re-normalises the up vectors, draws confidences ~ U(conf_lo, 1).
+ * camera (B,8), gravity (B,3) device pointers; outputs as in gclm_problem (any may be NULL).
+ */
+int gclm_render_fields(gclm_handle* h, int batch, int height, int width, int camera_model,
+                       const float* camera, const float* gravity, float sigma, float conf_lo,
+                       uint64_t seed, float* up_field, float* latitude_field, float* up_confidence,
+                       float* latitude_confidence, void* cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCLM_H_ */
