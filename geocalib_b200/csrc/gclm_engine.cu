@@ -36,6 +36,11 @@ namespace gclm {
 constexpr int PSTRIDE = 12;  // cam[8] + g[3] + pad
 constexpr unsigned FLAG_FROZEN = 0x100u;
 constexpr int MAX_WARPS = 10;
+// shared-intrinsics Schur partials per image (floats):
+//   [0,9) C  [9,18) E^T D~^-1 E  [18,21) g_c  [21,24) E^T D~^-1 g_g  [24] not-converged flag
+//   [25,31) W = D~^-1 E (2 x ni)  [31,33) wg = D~^-1 g_g
+constexpr int SCHUR_STRIDE = 48;
+constexpr int SCHUR_NSUM = 25;
 
 struct Ctrl {
   int stop;            // batch-global early stop fired: later LM passes are no-ops
@@ -251,6 +256,150 @@ __device__ __noinline__ void lm_step_image(const PassArgs& a, int b, const float
 }
 
 // ---------------------------------------------------------------------------------------------
+// shared intrinsics (lm_optimizer.py:350-383, 599-603).  The reference assembles the dense
+// (2B + ni)^2 arrow matrix [[blockdiag(D_i), E],[E^T, sum C_i]] and Choleskys it on the CPU.
+// Eliminating the per-image 2x2 gravity blocks gives the ni x ni Schur system
+//     (C~ - sum_i E_i^T D~_i^-1 E_i) dc = sum_i g_c,i - sum_i E_i^T D~_i^-1 g_g,i
+//     dg_i = D~_i^-1 (g_g,i - E_i dc)
+// with the same damping (diag += max(lambda diag, 1e-6), lambda fixed, :572-573,612).  Only the
+// <= 25 sums cross images (and GPUs): one tiny all-reduce per LM step.
+// ---------------------------------------------------------------------------------------------
+template <int MODEL>
+__device__ __noinline__ void schur_image(const PassArgs& a, int b, const float* sums) {
+  constexpr int NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH;
+  const float invN = 1.f / ((float)a.H * (float)a.W);
+  const float cu = sums[NH + NF] * (a.up_scale * a.up_scale) * invN;
+  const float cl = sums[NH + NF + 1] * (a.lat_scale * a.lat_scale) * invN;
+  const float cost = cu + cl;
+  bool converged = false;
+  if (a.pass == 0) { a.cost0[b * 3] = cost; a.cost0[b * 3 + 1] = cu; a.cost0[b * 3 + 2] = cl; }
+  else converged = allclose1(cost, a.prev_cost[b], a.atol, a.rtol);
+  a.prev_cost[b] = cost;
+  int act[NF];
+  const int n = active_columns(MODEL, a.est_gravity, a.est_focal, act);
+  const int ng = a.est_gravity ? 2 : 0, ni = n - ng;
+  float Hf[NF][NF];
+  {
+    int idx = 0;
+    for (int i = 0; i < NF; i++)
+      for (int j = i; j < NF; j++) { Hf[i][j] = sums[idx]; Hf[j][i] = sums[idx]; idx++; }
+  }
+  float* out = a.schur + (size_t)b * SCHUR_STRIDE;
+  for (int i = 0; i < SCHUR_STRIDE; i++) out[i] = 0.f;
+  const float lam = a.lambda0;
+  float Di[2][2] = {{0.f, 0.f}, {0.f, 0.f}};  // D~^-1
+  bool ok = true;
+  if (ng == 2) {
+    float d00 = Hf[0][0], d01 = Hf[0][1], d11 = Hf[1][1];
+    d00 += fmaxf(d00 * lam, 1e-6f);
+    d11 += fmaxf(d11 * lam, 1e-6f);
+    const float det = d00 * d11 - d01 * d01;
+    ok = (d00 > 0.f) && (det > 0.f);
+    if (ok) { Di[0][0] = d11 / det; Di[1][1] = d00 / det; Di[0][1] = Di[1][0] = -d01 / det; }
+    else a.flags[b] |= GCLM_STATUS_CHOLESKY_FAILED;
+  }
+  float W[2][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}}, wg[2] = {0.f, 0.f};
+  if (ng == 2 && ok) {
+    for (int j = 0; j < ni; j++) {
+      const float e0 = Hf[0][act[ng + j]], e1 = Hf[1][act[ng + j]];
+      W[0][j] = Di[0][0] * e0 + Di[0][1] * e1;
+      W[1][j] = Di[1][0] * e0 + Di[1][1] * e1;
+    }
+    const float g0 = sums[NH + 0], g1 = sums[NH + 1];
+    wg[0] = Di[0][0] * g0 + Di[0][1] * g1;
+    wg[1] = Di[1][0] * g0 + Di[1][1] * g1;
+  }
+  for (int i = 0; i < ni; i++) {
+    for (int j = 0; j < ni; j++) {
+      out[i * 3 + j] = Hf[act[ng + i]][act[ng + j]];
+      float ewe = 0.f;
+      if (ng == 2 && ok) ewe = Hf[0][act[ng + i]] * W[0][j] + Hf[1][act[ng + i]] * W[1][j];
+      out[9 + i * 3 + j] = ewe;
+    }
+    out[18 + i] = sums[NH + act[ng + i]];
+    out[21 + i] = (ng == 2 && ok) ? Hf[0][act[ng + i]] * wg[0] + Hf[1][act[ng + i]] * wg[1] : 0.f;
+  }
+  out[24] = (a.pass >= 1 && converged) ? 0.f : 1.f;
+  for (int j = 0; j < 3; j++) { out[25 + j] = W[0][j]; out[28 + j] = W[1][j]; }
+  out[31] = wg[0]; out[32] = wg[1];
+}
+
+// Sum the per-image Schur partials of this rank in a fixed order -> sum_out[SCHUR_NSUM].
+__global__ void __launch_bounds__(1024) shared_reduce_kernel(const PassArgs a, float* sum_out) {
+  __shared__ float s[32][SCHUR_NSUM];
+  if (*(volatile int*)&a.ctrl->stop) return;
+  const int j = threadIdx.x & 31, grp = threadIdx.x >> 5;
+  if (j < SCHUR_NSUM) {
+    float acc = 0.f;
+    for (int b = grp; b < a.B; b += 32) acc += a.schur[(size_t)b * SCHUR_STRIDE + j];
+    s[grp][j] = acc;
+  }
+  __syncthreads();
+  if (threadIdx.x < SCHUR_NSUM) {
+    float acc = 0.f;
+    for (int g = 0; g < 32; g++) acc += s[g][threadIdx.x];
+    sum_out[threadIdx.x] = acc;
+  }
+}
+
+// Every image redundantly solves the tiny Schur system and applies its own update.
+template <int MODEL>
+__global__ void shared_update_kernel(const PassArgs a, const float* sum_in) {
+  constexpr int K = Dims<MODEL>::K;
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (*(volatile int*)&a.ctrl->stop) return;
+  const int ng = a.est_gravity ? 2 : 0;
+  const int ni = (a.est_focal ? 1 : 0) + K;
+  float S[9], rhs[3];
+  for (int i = 0; i < ni; i++) {
+    for (int j = 0; j < ni; j++) S[i * ni + j] = sum_in[i * 3 + j];
+    rhs[i] = sum_in[18 + i] - sum_in[21 + i];
+  }
+  for (int i = 0; i < ni; i++) S[i * ni + i] += fmaxf(S[i * ni + i] * a.lambda0, 1e-6f);
+  for (int i = 0; i < ni; i++)
+    for (int j = 0; j < ni; j++) S[i * ni + j] -= sum_in[9 + i * 3 + j];
+  bool ok = true;
+  if (ni > 0) {
+    ok = cholesky(S, ni);
+    if (ok) cholesky_solve(S, ni, rhs);
+  }
+  if (!ok) for (int i = 0; i < 3; i++) rhs[i] = 0.f;  // zero step for everybody (:129-133)
+  const bool all_converged = a.pass >= 1 && sum_in[24] == 0.f;
+  if (b == 0 && all_converged) {
+    if (a.pass < a.ctrl->stop_at) a.ctrl->stop_at = a.pass;
+  }
+  if (b < a.B) {
+    const float* sc = a.schur + (size_t)b * SCHUR_STRIDE;
+    float d0 = 0.f, d1 = 0.f;
+    if (ng == 2 && ok) {
+      d0 = sc[31]; d1 = sc[32];
+      for (int j = 0; j < ni; j++) { d0 -= sc[25 + j] * rhs[j]; d1 -= sc[28 + j] * rhs[j]; }
+    }
+    if (!ok) a.flags[b] |= GCLM_STATUS_CHOLESKY_FAILED;
+    const int sl = a.slot[b];
+    const float* Pc = a.P + ((size_t)b * 2 + sl) * PSTRIDE;
+    float* Pn = a.P + ((size_t)b * 2 + (sl ^ 1)) * PSTRIDE;
+    float cam[8], g[3];
+    for (int i = 0; i < 8; i++) cam[i] = Pc[i];
+    for (int i = 0; i < 3; i++) g[i] = Pc[8 + i];
+    gravity_update(g, d0, d1, a.spherical);
+    int o = 0;
+    float df = 0.f;
+    if (a.est_focal) df = rhs[o++];
+    focal_update(cam, df, a.log_focal);
+    if (K > 0 && a.est_dist) dist_update(MODEL, cam, rhs + o);
+    for (int i = 0; i < 8; i++) Pn[i] = cam[i];
+    for (int i = 0; i < 3; i++) Pn[8 + i] = g[i];
+    a.slot[b] = sl ^ 1;
+  }
+}
+
+// Runs after shared_update_kernel of the same pass: latch the batch-global stop.
+__global__ void shared_stop_kernel(const PassArgs a, const float* sum_in) {
+  if (a.pass >= 1 && sum_in[24] == 0.f && a.early_stop) a.ctrl->stop = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
 // the fused pass kernel
 // ---------------------------------------------------------------------------------------------
 template <int MODEL, bool GEN_D, bool FULL>
@@ -358,7 +507,8 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) lm_pass_kernel(const PassArgs 
   }
   if (threadIdx.x == 0) {
     a.tickets[b] = 0u;
-    lm_step_image<MODEL>(a, b, s_sum);
+    if (a.shared && !a.is_final) schur_image<MODEL>(a, b, s_sum);
+    else lm_step_image<MODEL>(a, b, s_sum);
   }
 }
 
@@ -469,10 +619,46 @@ struct gclm_handle {
   char last_error[256] = {0};
 };
 
+// NCCL is bound at run time (dlopen) so that libgclm.so loads on boxes without NCCL / without a GPU.
+struct NcclUniqueId { char internal[GCLM_COMM_ID_BYTES]; };
+typedef int (*nccl_get_unique_id_t)(NcclUniqueId*);
+typedef int (*nccl_comm_init_rank_t)(void**, int, NcclUniqueId, int);
+typedef int (*nccl_all_reduce_t)(const void*, void*, size_t, int, int, void*, cudaStream_t);
+typedef int (*nccl_comm_destroy_t)(void*);
+typedef const char* (*nccl_get_error_string_t)(int);
+
+struct NcclApi {
+  void* lib = nullptr;
+  nccl_get_unique_id_t get_unique_id = nullptr;
+  nccl_comm_init_rank_t comm_init_rank = nullptr;
+  nccl_all_reduce_t all_reduce = nullptr;
+  nccl_comm_destroy_t comm_destroy = nullptr;
+  nccl_get_error_string_t get_error_string = nullptr;
+};
+
+static NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    // torch's bundled libnccl.so.2 is already mapped when the host framework is PyTorch
+    api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (api.lib) {
+      api.get_unique_id = (nccl_get_unique_id_t)dlsym(api.lib, "ncclGetUniqueId");
+      api.comm_init_rank = (nccl_comm_init_rank_t)dlsym(api.lib, "ncclCommInitRank");
+      api.all_reduce = (nccl_all_reduce_t)dlsym(api.lib, "ncclAllReduce");
+      api.comm_destroy = (nccl_comm_destroy_t)dlsym(api.lib, "ncclCommDestroy");
+      api.get_error_string = (nccl_get_error_string_t)dlsym(api.lib, "ncclGetErrorString");
+    }
+  }
+  const bool ok = api.lib && api.get_unique_id && api.comm_init_rank && api.all_reduce && api.comm_destroy;
+  return ok ? &api : nullptr;
+}
+
 struct gclm_comm {
-  void* nccl_lib = nullptr;
   void* comm = nullptr;
-  int world = 1, rank = 0;
+  int world = 1, rank = 0, device = 0;
 };
 
 #define CUDA_TRY(h, expr)                                                                  \
@@ -489,8 +675,6 @@ namespace {
 struct Layout {  // carve the scratch buffer
   size_t P, lam, prev, cost0, slot, flags, stop_at, tickets, ctrl, partials, schur, total;
 };
-
-constexpr int SCHUR_STRIDE = 48;
 
 struct TileCfg { int nwarps, rsub, rows_per_tile, tiles_per_image; };
 
@@ -713,21 +897,174 @@ int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt
 
 int gclm_solve_shared(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt,
                       const gclm_result* res, gclm_comm* comm, void* cuda_stream) {
-  (void)h; (void)prob; (void)opt; (void)res; (void)comm; (void)cuda_stream;
-  return GCLM_ERR_UNSUPPORTED;
+  if (!h || !res) return GCLM_ERR_INVALID_ARGUMENT;
+  int st = validate(prob, opt);
+  if (st != GCLM_OK) return st;
+  if (!prob->shared_intrinsics) return GCLM_ERR_INVALID_ARGUMENT;
+  NcclApi* nccl = nullptr;
+  if (comm && comm->world > 1) {
+    nccl = nccl_api();
+    if (!nccl) return GCLM_ERR_NCCL;
+  }
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  const TileCfg t = tile_config(prob->batch, prob->height, prob->width, h->num_sms, opt->rows_per_tile);
+  const Layout L = make_layout(prob->batch, std::max(t.tiles_per_image, max_tiles_for(prob->height, prob->width)));
+  st = ensure_scratch(h, L.total);
+  if (st != GCLM_OK) return st;
+  PassArgs a = make_args(h, prob, opt, res, t, L);
+  a.shared = 1;
+  a.stop_mode = GCLM_STOP_BATCH;  // shared intrinsics couple all images: the criterion is global
+  float* sums = a.schur + (size_t)prob->batch * SCHUR_STRIDE;  // 26 floats after the partials
+  const bool full = a.up && a.lat && a.uconf && a.lconf;
+  const unsigned bblocks = (unsigned)((prob->batch + 127) / 128);
+  lm_init_kernel<<<bblocks, 128, 0, s>>>(a, prob->camera_init, prob->gravity_init);
+  h->launches++;
+  const dim3 grid((unsigned)((size_t)prob->batch * t.tiles_per_image)), block(t.nwarps * 32);
+  for (int it = 0; it < opt->num_steps; it++) {
+    a.pass = it; a.is_final = 0;
+    launch_pass(a, !opt->use_log_focal, full, grid, block, s);
+    shared_reduce_kernel<<<1, 1024, 0, s>>>(a, sums);
+    if (nccl) {
+      const int rc = nccl->all_reduce(sums, sums, SCHUR_NSUM, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm->comm, s);
+      if (rc != 0) {
+        snprintf(h->last_error, sizeof(h->last_error), "ncclAllReduce: %s",
+                 nccl->get_error_string ? nccl->get_error_string(rc) : "error");
+        return GCLM_ERR_NCCL;
+      }
+    }
+    switch (a.model) {
+      case PINHOLE: shared_update_kernel<PINHOLE><<<bblocks, 128, 0, s>>>(a, sums); break;
+      case SIMPLE_RADIAL: shared_update_kernel<SIMPLE_RADIAL><<<bblocks, 128, 0, s>>>(a, sums); break;
+      case RADIAL: shared_update_kernel<RADIAL><<<bblocks, 128, 0, s>>>(a, sums); break;
+      default: shared_update_kernel<SIMPLE_DIVISIONAL><<<bblocks, 128, 0, s>>>(a, sums); break;
+    }
+    shared_stop_kernel<<<1, 1, 0, s>>>(a, sums);
+    h->launches += 4;
+  }
+  a.pass = opt->num_steps; a.is_final = 1;
+  launch_pass(a, true, full, grid, block, s);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GCLM_OK;
 }
 
-int gclm_comm_unique_id(void* id_out) { (void)id_out; return GCLM_ERR_UNSUPPORTED; }
+int gclm_comm_unique_id(void* id_out) {
+  if (!id_out) return GCLM_ERR_INVALID_ARGUMENT;
+  NcclApi* nccl = nccl_api();
+  if (!nccl) return GCLM_ERR_NCCL;
+  NcclUniqueId id;
+  if (nccl->get_unique_id(&id) != 0) return GCLM_ERR_NCCL;
+  memcpy(id_out, id.internal, GCLM_COMM_ID_BYTES);
+  return GCLM_OK;
+}
+
 int gclm_comm_create(const void* unique_id, int world_size, int rank, int device, gclm_comm** out) {
-  (void)unique_id; (void)world_size; (void)rank; (void)device; (void)out;
-  return GCLM_ERR_UNSUPPORTED;
+  if (!unique_id || !out || world_size < 1 || rank < 0 || rank >= world_size) return GCLM_ERR_INVALID_ARGUMENT;
+  *out = nullptr;
+  NcclApi* nccl = nccl_api();
+  if (!nccl) return GCLM_ERR_NCCL;
+  if (cudaSetDevice(device) != cudaSuccess) return GCLM_ERR_CUDA;
+  gclm_comm* c = new (std::nothrow) gclm_comm();
+  if (!c) return GCLM_ERR_OUT_OF_MEMORY;
+  c->world = world_size; c->rank = rank; c->device = device;
+  NcclUniqueId id;
+  memcpy(id.internal, unique_id, GCLM_COMM_ID_BYTES);
+  if (nccl->comm_init_rank(&c->comm, world_size, id, rank) != 0) { delete c; return GCLM_ERR_NCCL; }
+  *out = c;
+  return GCLM_OK;
 }
-int gclm_comm_destroy(gclm_comm* c) { (void)c; return GCLM_OK; }
 
+int gclm_comm_destroy(gclm_comm* c) {
+  if (!c) return GCLM_OK;
+  NcclApi* nccl = nccl_api();
+  if (nccl && c->comm) nccl->comm_destroy(c->comm);
+  delete c;
+  return GCLM_OK;
+}
+
+// ---- host-buffer path: chunked, H2D of chunk i+1 overlaps the solve of chunk i ----
 int gclm_solve_host(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt,
                     const gclm_result* res, int chunk_images) {
-  (void)h; (void)prob; (void)opt; (void)res; (void)chunk_images;
-  return GCLM_ERR_UNSUPPORTED;
+  if (!h || !res) return GCLM_ERR_INVALID_ARGUMENT;
+  int st = validate(prob, opt);
+  if (st != GCLM_OK) return st;
+  if (prob->shared_intrinsics) return GCLM_ERR_UNSUPPORTED;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const int B = prob->batch, H = prob->height, W = prob->width;
+  const size_t N = (size_t)H * W;
+  const int chunk = std::max(1, std::min(chunk_images > 0 ? chunk_images : 128, B));
+  const int n = gclm_num_params(prob->camera_model, prob->estimate_gravity, prob->estimate_focal);
+  // staging layout per buffer (floats): up 2N | lat N | uconf N | lconf N | cam 8 | grav 3 | results
+  const size_t in_f = (size_t)chunk * (5 * N + 11);
+  const size_t res_f = (size_t)chunk * (8 + 3 + 2 * n * n + 5 + 6 + 2);
+  const size_t buf_bytes = ((in_f + res_f) * sizeof(float) + 255) & ~size_t(255);
+  if (h->stage_bytes < buf_bytes) {
+    for (int i = 0; i < 2; i++) { if (h->stage[i]) cudaFree(h->stage[i]); h->stage[i] = nullptr; }
+    h->stage_bytes = 0;
+    for (int i = 0; i < 2; i++) CUDA_TRY(h, cudaMalloc(&h->stage[i], buf_bytes));
+    h->stage_bytes = buf_bytes;
+  }
+  for (int i = 0; i < 2; i++) {
+    if (!h->hstream[i]) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->hstream[i], cudaStreamNonBlocking));
+    if (!h->hevent[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&h->hevent[i], cudaEventDisableTiming));
+  }
+  cudaStream_t s_copy = h->hstream[0], s_comp = h->hstream[1];
+  cudaEvent_t ready[2], freed[2] = {h->hevent[0], h->hevent[1]};
+  for (int i = 0; i < 2; i++) CUDA_TRY(h, cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming));
+  st = gclm_reserve(h, chunk, H, W);
+  int rc = st;
+  for (int s0 = 0, i = 0; s0 < B && rc == GCLM_OK; s0 += chunk, i++) {
+    const int c = std::min(chunk, B - s0), k = i & 1;
+    float* base = static_cast<float*>(h->stage[k]);
+    float *d_up = base, *d_lat = d_up + (size_t)chunk * 2 * N, *d_uc = d_lat + (size_t)chunk * N;
+    float *d_lc = d_uc + (size_t)chunk * N, *d_cam = d_lc + (size_t)chunk * N, *d_g = d_cam + (size_t)chunk * 8;
+    float* d_res = d_g + (size_t)chunk * 3;
+    if (i >= 2) cudaStreamWaitEvent(s_copy, freed[k], 0);
+    auto h2d = [&](float* dst, const float* src, size_t per_image) {
+      if (src) cudaMemcpyAsync(dst, src + (size_t)s0 * per_image, (size_t)c * per_image * sizeof(float),
+                               cudaMemcpyHostToDevice, s_copy);
+    };
+    h2d(d_up, prob->up_field, 2 * N); h2d(d_lat, prob->latitude_field, N);
+    h2d(d_uc, prob->up_confidence, N); h2d(d_lc, prob->latitude_confidence, N);
+    h2d(d_cam, prob->camera_init, 8); h2d(d_g, prob->gravity_init, 3);
+    cudaEventRecord(ready[k], s_copy);
+    cudaStreamWaitEvent(s_comp, ready[k], 0);
+    gclm_problem p = *prob;
+    p.batch = c;
+    p.up_field = prob->up_field ? d_up : nullptr; p.latitude_field = prob->latitude_field ? d_lat : nullptr;
+    p.up_confidence = prob->up_confidence ? d_uc : nullptr;
+    p.latitude_confidence = prob->latitude_confidence ? d_lc : nullptr;
+    p.camera_init = d_cam; p.gravity_init = d_g;
+    gclm_result r;
+    float* q = d_res;
+    r.camera = q; q += (size_t)chunk * 8;
+    r.gravity = q; q += (size_t)chunk * 3;
+    r.covariance = q; q += (size_t)chunk * n * n;
+    r.hessian_rpf = q; q += (size_t)chunk * n * n;
+    r.uncertainty = q; q += (size_t)chunk * 5;
+    r.costs = q; q += (size_t)chunk * 6;
+    r.stop_at = reinterpret_cast<int32_t*>(q); q += chunk;
+    r.status = reinterpret_cast<uint32_t*>(q);
+    rc = gclm_solve(h, &p, opt, &r, s_comp);
+    if (rc != GCLM_OK) break;
+    auto d2h = [&](void* dst, const void* src, size_t per_image_bytes) {
+      if (dst) cudaMemcpyAsync(static_cast<char*>(dst) + (size_t)s0 * per_image_bytes, src,
+                               (size_t)c * per_image_bytes, cudaMemcpyDeviceToHost, s_comp);
+    };
+    d2h(res->camera, r.camera, 8 * sizeof(float)); d2h(res->gravity, r.gravity, 3 * sizeof(float));
+    d2h(res->covariance, r.covariance, (size_t)n * n * sizeof(float));
+    d2h(res->hessian_rpf, r.hessian_rpf, (size_t)n * n * sizeof(float));
+    d2h(res->uncertainty, r.uncertainty, 5 * sizeof(float)); d2h(res->costs, r.costs, 6 * sizeof(float));
+    d2h(res->stop_at, r.stop_at, sizeof(int32_t)); d2h(res->status, r.status, sizeof(uint32_t));
+    cudaEventRecord(freed[k], s_comp);
+  }
+  cudaError_t e = cudaStreamSynchronize(s_comp);
+  cudaStreamSynchronize(s_copy);
+  for (int i = 0; i < 2; i++) cudaEventDestroy(ready[i]);
+  if (rc != GCLM_OK) return rc;
+  if (e != cudaSuccess) { snprintf(h->last_error, sizeof(h->last_error), "%s", cudaGetErrorString(e)); return GCLM_ERR_CUDA; }
+  return GCLM_OK;
 }
 
 int gclm_render_fields(gclm_handle* h, int batch, int height, int width, int camera_model,

@@ -124,8 +124,9 @@ class Engine:
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         with torch.cuda.device(dev):
             if shared_intrinsics:
+                comm_h = getattr(comm, "handle", comm)
                 st = self.lib.gclm_solve_shared(self._h, ctypes.byref(prob), ctypes.byref(opt),
-                                                ctypes.byref(res), comm, stream)
+                                                ctypes.byref(res), comm_h, stream)
                 _lib.check(st, "gclm_solve_shared")
             else:
                 st = self.lib.gclm_solve(self._h, ctypes.byref(prob), ctypes.byref(opt),
@@ -156,4 +157,50 @@ class Engine:
         out = {"up_field": up, "latitude_field": lat}
         if with_confidence:
             out |= {"up_confidence": uc, "latitude_confidence": lc}
+        return out
+
+    # ------------------------------------------------------------------------------------------
+    def solve_host(self, camera_model: str, host_fields: Dict[str, torch.Tensor],
+                   camera_init: torch.Tensor, gravity_init: torch.Tensor, *,
+                   options: Optional[Options] = None, estimate_gravity: bool = True,
+                   estimate_focal: bool = True, estimate_dist: bool = True, chunk_images: int = 128,
+                   out: Optional[Dict[str, torch.Tensor]] = None) -> Dict[str, torch.Tensor]:
+        """gclm_solve_host: HOST (ideally pinned) float32 tensors in, host tensors out; the library
+        pipelines H2D / solve / D2H over chunks.  Synchronous."""
+        ref = host_fields.get("up_field", host_fields.get("latitude_field"))
+        if ref is None:
+            raise _lib.GclmError("need at least one of up_field / latitude_field")
+        B, _, H, W = ref.shape
+        opt = options if options is not None else _lib.default_options()
+        n = 2 * int(estimate_gravity) + int(estimate_focal) + NUM_DIST[camera_model]
+
+        def hp(t, shape, name):
+            if t is None:
+                return None
+            if t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or tuple(t.shape) != tuple(shape):
+                raise _lib.GclmError(f"{name}: expected a contiguous float32 CPU tensor of shape {tuple(shape)}")
+            return t.data_ptr()
+
+        prob = Problem(
+            batch=B, height=H, width=W, camera_model=CAMERA_MODEL_IDS[camera_model],
+            up_field=hp(host_fields.get("up_field"), (B, 2, H, W), "up_field"),
+            latitude_field=hp(host_fields.get("latitude_field"), (B, 1, H, W), "latitude_field"),
+            up_confidence=hp(host_fields.get("up_confidence"), (B, H, W), "up_confidence"),
+            latitude_confidence=hp(host_fields.get("latitude_confidence"), (B, H, W), "latitude_confidence"),
+            camera_init=hp(camera_init, (B, 8), "camera_init"), gravity_init=hp(gravity_init, (B, 3), "gravity_init"),
+            estimate_gravity=int(estimate_gravity), estimate_focal=int(estimate_focal),
+            estimate_dist=int(estimate_dist), shared_intrinsics=0,
+        )
+        if out is None:
+            pin = lambda *shape, dtype=torch.float32: torch.empty(shape, dtype=dtype).pin_memory()
+            out = {
+                "camera": pin(B, 8), "gravity": pin(B, 3), "covariance": pin(B, n, n), "uncertainty": pin(B, 5),
+                "costs": pin(B, 6), "stop_at": pin(B, dtype=torch.int32), "status": pin(B, dtype=torch.int32),
+                "hessian_rpf": pin(B, n, n),
+            }
+        res = Result(**{k: out[k].data_ptr() for k in
+                        ("camera", "gravity", "covariance", "uncertainty", "costs", "stop_at", "status", "hessian_rpf")})
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.gclm_solve_host(self._h, ctypes.byref(prob), ctypes.byref(opt),
+                                                ctypes.byref(res), int(chunk_images)), "gclm_solve_host")
         return out
