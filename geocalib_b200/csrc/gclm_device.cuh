@@ -57,15 +57,14 @@ __device__ __forceinline__ float sin_poly(float x) {
   p = fmaf(p, z, -1.6666665857e-01f);
   return fmaf(x * z, p, x);
 }
-// Cold path: any of the four latitudes is outside the polynomial's range -> exact sinf for all.
-__device__ __noinline__ void sin4_slow(const float4 x, float (&s)[4]) {
-  s[0] = sinf(x.x); s[1] = sinf(x.y); s[2] = sinf(x.z); s[3] = sinf(x.w);
-}
+// Cold path (latitude outside the polynomial's range): exact sinf.  Scalar in / scalar out so that
+// nothing in the hot loop has its address taken (an array argument here costs STL/LDL per row).
+__device__ __noinline__ float sin_slow(float x) { return sinf(x); }
 // target_lat = sin(latitude_field) for 4 pixels (lm_optimizer.py:270)
-__device__ __forceinline__ void sin4(const float4 x, float (&s)[4]) {
-  s[0] = sin_poly(x.x); s[1] = sin_poly(x.y); s[2] = sin_poly(x.z); s[3] = sin_poly(x.w);
+__device__ __forceinline__ void sin4(const float4 x, float& s0, float& s1, float& s2, float& s3) {
+  s0 = sin_poly(x.x); s1 = sin_poly(x.y); s2 = sin_poly(x.z); s3 = sin_poly(x.w);
   const float mx = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));
-  if (mx > 1.6f) sin4_slow(x, s);
+  if (mx > 1.6f) { s0 = sin_slow(x.x); s1 = sin_slow(x.y); s2 = sin_slow(x.z); s3 = sin_slow(x.w); }
 }
 
 // ------------------------------------------------------------------------------------------

@@ -460,12 +460,12 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) lm_pass_kernel(const PassArgs 
       if (FULL || fm.up_conf) { cu = ldg_stream(p_cu); p_cu += W; }
       if (FULL || fm.lat_conf) { cl = ldg_stream(p_cl); p_cl += W; }
       const float v = ((float)y - pc.cy) * pc.inv_fy;
-      float sl[4] = {0.f, 0.f, 0.f, 0.f};
-      if (FULL || fm.lat) sin4(ol, sl);
-      pixel_accumulate<MODEL, GEN_D, FULL>(pc, fm, u[0], v, ox.x, oy.x, sl[0], cu.x, cl.x, inv_up2, inv_lat2, acc);
-      pixel_accumulate<MODEL, GEN_D, FULL>(pc, fm, u[1], v, ox.y, oy.y, sl[1], cu.y, cl.y, inv_up2, inv_lat2, acc);
-      pixel_accumulate<MODEL, GEN_D, FULL>(pc, fm, u[2], v, ox.z, oy.z, sl[2], cu.z, cl.z, inv_up2, inv_lat2, acc);
-      pixel_accumulate<MODEL, GEN_D, FULL>(pc, fm, u[3], v, ox.w, oy.w, sl[3], cu.w, cl.w, inv_up2, inv_lat2, acc);
+      float sl0 = 0.f, sl1 = 0.f, sl2 = 0.f, sl3 = 0.f;
+      if (FULL || fm.lat) sin4(ol, sl0, sl1, sl2, sl3);
+      pixel_accumulate<MODEL, GEN_D, FULL>(pc, fm, u[0], v, ox.x, oy.x, sl0, cu.x, cl.x, inv_up2, inv_lat2, acc);
+      pixel_accumulate<MODEL, GEN_D, FULL>(pc, fm, u[1], v, ox.y, oy.y, sl1, cu.y, cl.y, inv_up2, inv_lat2, acc);
+      pixel_accumulate<MODEL, GEN_D, FULL>(pc, fm, u[2], v, ox.z, oy.z, sl2, cu.z, cl.z, inv_up2, inv_lat2, acc);
+      pixel_accumulate<MODEL, GEN_D, FULL>(pc, fm, u[3], v, ox.w, oy.w, sl3, cu.w, cl.w, inv_up2, inv_lat2, acc);
     }
   }
 

@@ -248,9 +248,18 @@ def test_optional_inputs_and_priors_vs_oracle(dev, model):
                         fn["latitude_field"] if "latitude_field" in data else None,
                         fn["up_confidence"] if "up_confidence" in data else None,
                         fn["latitude_confidence"] if "latitude_confidence" in data else None, conf=conf, **pri)
-        assert_params_close(out["camera"]._data.cpu().numpy(), out["gravity"]._data.cpu().numpy(),
-                            ref["camera"], ref["gravity"], model)
+        np.testing.assert_allclose(out["final_cost"].cpu().numpy(), ref["final_cost"], rtol=1e-3, err_msg=name)
         assert out["covariance"].shape == ref["covariance"].shape, name
+        if name == "uponly":
+            # not reachable in the reference (lm_optimizer.py:31 needs latitude_field); the focal
+            # is barely observable from the up field alone, so only the well-posed part is compared
+            assert np.abs(out["gravity"]._data.cpu().numpy() - ref["gravity"]).max() < 2e-3, name
+            continue
+        try:
+            assert_params_close(out["camera"]._data.cpu().numpy(), out["gravity"]._data.cpu().numpy(),
+                                ref["camera"], ref["gravity"], model)
+        except AssertionError as e:
+            raise AssertionError(f"case {name}: {e}") from e
 
 
 # ------------------------------------------------------------------------------------------------
@@ -421,7 +430,9 @@ def test_host_path_matches_device_path(dev, model):
     h, w, B = 96, 128, 11
     cam, grav = synth_params(model, B, h, w, 2)
     f = render_on_device(model, cam, grav, h, w, dev, sigma=0.02, seed=8)
-    opt = G.LMOptimizer({"camera_model": model, "num_steps": 12, "early_stop": False}).eval()
+    # rows_per_tile pinned: the auto tiling depends on the batch size, and with it the summation
+    # order; with a fixed tiling the chunked host path is BIT-identical to the one-shot device path
+    opt = G.LMOptimizer({"camera_model": model, "num_steps": 12, "early_stop": False, "rows_per_tile": 32}).eval()
     with torch.no_grad():
         ref = opt(f)
     torch.cuda.synchronize()
