@@ -164,8 +164,15 @@ def cpu_run(model, fields, iters):
     return time.perf_counter() - t
 
 
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_baseline(model, h, w, iters, target_seconds=15.0):
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     probe_n = max(2, min(cores, 8))
     fields = cpu_sample_fields(model, probe_n, h, w, 99)
     dt = cpu_run(model, fields, iters)
@@ -187,7 +194,7 @@ def run_reference_arm(args, wl):
     if rank != 0:
         return
     model, B, h, w, iters = wl
-    cores = os.cpu_count() or 1
+    cores = host_threads()
     n = max(2, min(cores, 16))
     fields = cpu_sample_fields(model, n, h, w, 99)
     probe = cpu_run(model, fields, iters)

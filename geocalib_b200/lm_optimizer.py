@@ -40,6 +40,9 @@ UNCERTAINTY_KEYS = ("roll_uncertainty", "pitch_uncertainty", "gravity_uncertaint
                     "focal_uncertainty", "vfov_uncertainty")
 
 
+_INIT_CACHE: Dict[tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
+
+
 def get_trivial_estimation(data: Dict[str, torch.Tensor], camera_model) -> Tuple[torch.Tensor, torch.Tensor]:
     """Initial estimate (reference: lm_optimizer.py:20-58): roll = pitch = 0, f = 0.7 max(h, w)
     passed through a vfov round trip, fx rescaled by `scales`, priors override.
@@ -50,6 +53,10 @@ def get_trivial_estimation(data: Dict[str, torch.Tensor], camera_model) -> Tuple
     ref = ref.detach()
     B = ref.shape[0]
     h, w = ref.shape[-2:]
+    plain = not any(k in data for k in ("prior_focal", "prior_gravity", "prior_dist", "scales"))
+    key = (B, h, w, str(ref.device), camera_model.name())
+    if plain and key in _INIT_CACHE:  # the prior-free estimate depends on the shape only
+        return _INIT_CACHE[key]
     hh, ww = ref.new_full((B,), float(h)), ref.new_full((B,), float(w))
     focal = data["prior_focal"] if "prior_focal" in data else 0.7 * torch.max(hh, ww)
     params = {"width": ww, "height": hh, "vfov": focal2fov(focal.to(ref), h)}
@@ -67,7 +74,12 @@ def get_trivial_estimation(data: Dict[str, torch.Tensor], camera_model) -> Tuple
     else:
         zeros = ref.new_zeros((B,))
         grav = Gravity.from_rp(zeros, zeros)._data.float()
-    return cam.contiguous(), grav.reshape(B, 3).contiguous()
+    out = cam.contiguous(), grav.reshape(B, 3).contiguous()
+    if plain:
+        if len(_INIT_CACHE) > 64:
+            _INIT_CACHE.clear()
+        _INIT_CACHE[key] = out
+    return out
 
 
 class LMOptimizer(nn.Module):

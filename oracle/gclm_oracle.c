@@ -37,6 +37,11 @@
 #include <stdlib.h>
 #include <string.h>
 #include <tgmath.h>
+#ifdef _OPENMP
+#include <omp.h>
+#else
+static int omp_get_max_threads(void) { return 1; }
+#endif
 
 #ifndef REAL
 #define REAL float
@@ -648,7 +653,7 @@ int FN(gclm_oracle_lm)(const oracle_conf *c, const REAL *up, const REAL *lat, co
   for (int it = 0; it < c->num_steps; it++) {
     iters = it + 1;
     /* residuals + costs + system at the current estimate */
-#pragma omp parallel for schedule(dynamic) if (B > 1)
+#pragma omp parallel for schedule(dynamic) if (B >= omp_get_max_threads())
     for (int b = 0; b < B; b++)
       if (!frozen[b]) eval_image(&ims[b], cam + 8 * b, grav + 3 * b, 0, c->spherical, c->log_focal, 1, &sys[b]);
     if (it == 0)
@@ -721,7 +726,7 @@ int FN(gclm_oracle_lm)(const oracle_conf *c, const REAL *up, const REAL *lat, co
       if (K > 0 && c->apply_dist) update_dist(c->model, cam + 8 * b, d + o);
     }
     /* ---- new cost (lm_optimizer.py:607-610) ---- */
-#pragma omp parallel for schedule(dynamic) if (B > 1)
+#pragma omp parallel for schedule(dynamic) if (B >= omp_get_max_threads())
     for (int b = 0; b < B; b++)
       if (!frozen[b]) {
         image_sys s;
@@ -769,7 +774,7 @@ int FN(gclm_oracle_lm)(const oracle_conf *c, const REAL *up, const REAL *lat, co
   if (c->global_semantics) for (int b = 0; b < B; b++) out_stop_at[b] = stop_global;
 
   /* ---- final costs + uncertainty (lm_optimizer.py:632-642, 463-516) ---- */
-#pragma omp parallel for schedule(dynamic) if (B > 1)
+#pragma omp parallel for schedule(dynamic) if (B >= omp_get_max_threads())
   for (int b = 0; b < B; b++) {
     image_sys s;
     eval_image(&ims[b], cam + 8 * b, grav + 3 * b, 1, c->spherical, c->log_focal, c->compute_uncertainty, &s);
