@@ -481,6 +481,56 @@ static void eval_image(const image_in *im, const REAL cam[8], const REAL g[3], i
   out->cost_lat = (REAL)(cost[1] / N);
 }
 
+/* Batch version: one flat OpenMP loop over (image, 8-row chunk) tasks so that any batch size uses
+ * all host threads; per-image partials are then added in chunk order (thread-count independent). */
+static void eval_batch(const image_in *ims, int B, const char *skip, const REAL *cam, const REAL *grav,
+                       int rpf_basis, int spherical, int log_focal, int want_jac, image_sys *out) {
+  const int chunk = 8, H = ims[0].H;
+  const int nchunks = (H + chunk - 1) / chunk;
+  const size_t stride = MAXF + MAXF * MAXF + 2;
+  double *pg = (double *)calloc((size_t)B * nchunks * stride, sizeof(double));
+  REAL (*Ts)[3][2] = malloc(sizeof(REAL[3][2]) * B);
+  REAL (*fs)[2] = malloc(sizeof(REAL[2]) * B);
+  for (int b = 0; b < B; b++) {
+    const REAL *g = grav + 3 * b, *cm = cam + 8 * b;
+    if (spherical && !rpf_basis) tangent_spherical(g, Ts[b]); else tangent_rp(g, Ts[b]);
+    if (log_focal && !rpf_basis) { fs[b][0] = fs[b][1] = R(1); }
+    else { fs[b][0] = R(1) / cm[2]; fs[b][1] = R(1) / cm[3]; }
+  }
+#pragma omp parallel for schedule(dynamic, 4)
+  for (long t = 0; t < (long)B * nchunks; t++) {
+    const int b = (int)(t / nchunks), c = (int)(t % nchunks);
+    if (skip && skip[b]) continue;
+    double *q = pg + (size_t)t * stride;
+    double lG[MAXF] = {0}, lH[MAXF][MAXF] = {{0}}, lc[2] = {0, 0};
+    const int y0 = c * chunk, y1 = (y0 + chunk < H) ? y0 + chunk : H;
+    accumulate_rows(&ims[b], y0, y1, cam + 8 * b, grav + 3 * b, Ts[b], fs[b], want_jac, lG, lH, lc);
+    memcpy(q, lG, sizeof(lG));
+    memcpy(q + MAXF, lH, sizeof(lH));
+    q[MAXF + MAXF * MAXF] = lc[0]; q[MAXF + MAXF * MAXF + 1] = lc[1];
+  }
+  const double N = (double)H * ims[0].W;
+  for (int b = 0; b < B; b++) {
+    if (skip && skip[b]) continue;
+    double G[MAXF] = {0}, Hs[MAXF][MAXF] = {{0}}, cost[2] = {0, 0};
+    for (int c = 0; c < nchunks; c++) {
+      const double *q = pg + ((size_t)b * nchunks + c) * stride;
+      for (int a = 0; a < MAXF; a++) {
+        G[a] += q[a];
+        for (int k = 0; k < MAXF; k++) Hs[a][k] += q[MAXF + a * MAXF + k];
+      }
+      cost[0] += q[MAXF + MAXF * MAXF]; cost[1] += q[MAXF + MAXF * MAXF + 1];
+    }
+    for (int a = 0; a < MAXF; a++) {
+      out[b].G[a] = (REAL)G[a];
+      for (int k = 0; k < MAXF; k++) out[b].H[a][k] = (REAL)Hs[a][k];
+    }
+    out[b].cost_up = (REAL)(cost[0] / N);
+    out[b].cost_lat = (REAL)(cost[1] / N);
+  }
+  free(pg); free(Ts); free(fs);
+}
+
 /* ---------------- linear algebra ---------------- */
 
 /* In-place Cholesky (lower) of an n x n SPD matrix stored with leading dim ld. 0 = ok. */
@@ -645,6 +695,7 @@ int FN(gclm_oracle_lm)(const oracle_conf *c, const REAL *up, const REAL *lat, co
   REAL *prev_cost = (REAL *)calloc(B, sizeof(REAL));
   REAL *new_cost = (REAL *)calloc(B, sizeof(REAL));
   image_sys *sys = (image_sys *)malloc(sizeof(image_sys) * B);
+  image_sys *sys2 = (image_sys *)malloc(sizeof(image_sys) * B);
   REAL *delta = (REAL *)calloc((size_t)B * MAXF, sizeof(REAL)); /* per-image active-order */
   char *frozen = (char *)calloc(B, 1);
   int stop_global = c->num_steps, iters = 0;
@@ -653,9 +704,7 @@ int FN(gclm_oracle_lm)(const oracle_conf *c, const REAL *up, const REAL *lat, co
   for (int it = 0; it < c->num_steps; it++) {
     iters = it + 1;
     /* residuals + costs + system at the current estimate */
-#pragma omp parallel for schedule(dynamic) if (B >= omp_get_max_threads())
-    for (int b = 0; b < B; b++)
-      if (!frozen[b]) eval_image(&ims[b], cam + 8 * b, grav + 3 * b, 0, c->spherical, c->log_focal, 1, &sys[b]);
+    eval_batch(ims, B, frozen, cam, grav, 0, c->spherical, c->log_focal, 1, sys);
     if (it == 0)
       for (int b = 0; b < B; b++) {
         prev_cost[b] = sys[b].cost_up + sys[b].cost_lat;
@@ -726,13 +775,9 @@ int FN(gclm_oracle_lm)(const oracle_conf *c, const REAL *up, const REAL *lat, co
       if (K > 0 && c->apply_dist) update_dist(c->model, cam + 8 * b, d + o);
     }
     /* ---- new cost (lm_optimizer.py:607-610) ---- */
-#pragma omp parallel for schedule(dynamic) if (B >= omp_get_max_threads())
+    eval_batch(ims, B, frozen, cam, grav, 0, c->spherical, c->log_focal, 0, sys2);
     for (int b = 0; b < B; b++)
-      if (!frozen[b]) {
-        image_sys s;
-        eval_image(&ims[b], cam + 8 * b, grav + 3 * b, 0, c->spherical, c->log_focal, 0, &s);
-        new_cost[b] = s.cost_up + s.cost_lat;
-      }
+      if (!frozen[b]) new_cost[b] = sys2[b].cost_up + sys2[b].cost_lat;
     /* ---- lambda (lm_optimizer.py:95-106, 612-613) ---- */
     if (!c->fix_lambda && !c->shared_intrinsics)
       for (int b = 0; b < B; b++) {
@@ -774,10 +819,9 @@ int FN(gclm_oracle_lm)(const oracle_conf *c, const REAL *up, const REAL *lat, co
   if (c->global_semantics) for (int b = 0; b < B; b++) out_stop_at[b] = stop_global;
 
   /* ---- final costs + uncertainty (lm_optimizer.py:632-642, 463-516) ---- */
-#pragma omp parallel for schedule(dynamic) if (B >= omp_get_max_threads())
+  eval_batch(ims, B, NULL, cam, grav, 1, c->spherical, c->log_focal, c->compute_uncertainty, sys2);
   for (int b = 0; b < B; b++) {
-    image_sys s;
-    eval_image(&ims[b], cam + 8 * b, grav + 3 * b, 1, c->spherical, c->log_focal, c->compute_uncertainty, &s);
+    const image_sys s = sys2[b];
     out_costs[6 * b + 3] = s.cost_up + s.cost_lat;
     out_costs[6 * b + 4] = s.cost_up;
     out_costs[6 * b + 5] = s.cost_lat;
@@ -805,7 +849,7 @@ int FN(gclm_oracle_lm)(const oracle_conf *c, const REAL *up, const REAL *lat, co
       unc[4] = sqrt(jf * jf * cff / R(2));
     }
   }
-  free(ims); free(lamb); free(prev_cost); free(new_cost); free(sys); free(delta); free(frozen);
+  free(ims); free(lamb); free(prev_cost); free(new_cost); free(sys); free(sys2); free(delta); free(frozen);
   return iters;
 }
 

@@ -440,7 +440,8 @@ def test_host_path_matches_device_path(dev, model):
     for chunk in (4, 11, 64):
         res = HostPipeline(opt, B, h, w, chunk, dev).run(host)
         assert torch.equal(res["camera"], ref["camera"]._data.cpu()), chunk
-        assert torch.equal(res["gravity"], ref["gravity"]._data.cpu())
+        # the Gravity container re-normalises the raw engine output (gravity.py:26): last-bit only
+        assert torch.allclose(res["gravity"], ref["gravity"]._data.cpu(), rtol=0, atol=2e-7)
         assert torch.equal(res["covariance"], ref["covariance"].cpu())
         assert torch.equal(res["costs"][:, 3], ref["final_cost"].cpu())
 
