@@ -16,6 +16,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 namespace gclm {
 
 enum : int { PINHOLE = 0, SIMPLE_RADIAL = 1, RADIAL = 2, SIMPLE_DIVISIONAL = 3 };
@@ -47,6 +49,57 @@ __device__ __forceinline__ float fast_rcp(float x) {
   return y;
 }
 
+// ------------------------------------------------------------------------------------------
+// f2: two pixels per register pair.  Blackwell (sm_100) has packed fp32x2 arithmetic
+// (PTX fma.rn.f32x2 / mul / add -> SASS FFMA2 / FMUL2 / FADD2, operands may be a register pair,
+// a broadcast scalar or a uniform register, each with a negate modifier): one issue slot per two
+// pixels.  Measured on B200 (tools/ubench_fp32x2.cu): FMUL2/FADD2 issue at the scalar rate
+// (2x flops), FFMA2 at ~0.55x the scalar rate (1.1x flops) -- the pass kernel is issue-bound, so
+// halving the issue slots of ~80 % of its instructions is what matters.
+// The same source below compiles for V = float (one pixel) and V = f2 (two pixels).
+// ------------------------------------------------------------------------------------------
+// keep the scalar math functions visible next to the packed overloads declared below
+using ::fmaf;
+using ::fmaxf;
+using ::fminf;
+
+struct f2 {
+  float2 v;
+  __device__ __forceinline__ f2() {}
+  __device__ __forceinline__ explicit f2(float s) : v(make_float2(s, s)) {}
+  __device__ __forceinline__ f2(float a, float b) : v(make_float2(a, b)) {}
+  __device__ __forceinline__ explicit f2(float2 a) : v(a) {}
+};
+__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
+__device__ __forceinline__ float2 bc2(f2 a) { return a.v; }
+template <class T> struct is_f2 { static constexpr bool value = false; };
+template <> struct is_f2<f2> { static constexpr bool value = true; };
+#define GCLM_ANY_F2_2(A, B) typename = typename std::enable_if<is_f2<A>::value || is_f2<B>::value>::type
+#define GCLM_ANY_F2_3(A, B, C) \
+  typename = typename std::enable_if<is_f2<A>::value || is_f2<B>::value || is_f2<C>::value>::type
+
+template <class A, class B, GCLM_ANY_F2_2(A, B)>
+__device__ __forceinline__ f2 operator*(A a, B b) { return f2(__fmul2_rn(bc2(a), bc2(b))); }
+template <class A, class B, GCLM_ANY_F2_2(A, B)>
+__device__ __forceinline__ f2 operator+(A a, B b) { return f2(__fadd2_rn(bc2(a), bc2(b))); }
+__device__ __forceinline__ f2 operator-(f2 a) { return f2(-a.v.x, -a.v.y); }
+template <class A, class B, GCLM_ANY_F2_2(A, B)>
+__device__ __forceinline__ f2 operator-(A a, B b) {
+  const float2 nb = bc2(b);
+  return f2(__fadd2_rn(bc2(a), make_float2(-nb.x, -nb.y)));
+}
+template <class A, class B, class C, GCLM_ANY_F2_3(A, B, C)>
+__device__ __forceinline__ f2 fmaf(A a, B b, C c) { return f2(__ffma2_rn(bc2(a), bc2(b), bc2(c))); }
+__device__ __forceinline__ f2 fmaxf(f2 a, float s) { return f2(::fmaxf(a.v.x, s), ::fmaxf(a.v.y, s)); }
+__device__ __forceinline__ f2 fminf(f2 a, float s) { return f2(::fminf(a.v.x, s), ::fminf(a.v.y, s)); }
+__device__ __forceinline__ f2 fast_rsqrt(f2 a) { return f2(fast_rsqrt(a.v.x), fast_rsqrt(a.v.y)); }
+__device__ __forceinline__ f2 fast_rcp(f2 a) { return f2(fast_rcp(a.v.x), fast_rcp(a.v.y)); }
+__device__ __forceinline__ float hsum(float a) { return a; }
+__device__ __forceinline__ float hsum(f2 a) { return a.v.x + a.v.y; }
+template <class V> __device__ __forceinline__ V splat(float s);
+template <> __device__ __forceinline__ float splat<float>(float s) { return s; }
+template <> __device__ __forceinline__ f2 splat<f2>(float s) { return f2(s); }
+
 // sin(x) for |x| <= 1.6 (latitudes live in [-pi/2, pi/2]): degree-9 odd polynomial, max abs
 // error 1.5e-7 against fp64 sin (coefficients: Chebyshev fit of (sin(x)/x - 1)/x^2 in x^2).
 __device__ __forceinline__ float sin_poly(float x) {
@@ -61,8 +114,17 @@ __device__ __forceinline__ float sin_poly(float x) {
 // nothing in the hot loop has its address taken (an array argument here costs STL/LDL per row).
 __device__ __noinline__ float sin_slow(float x) { return sinf(x); }
 // target_lat = sin(latitude_field) for 4 pixels (lm_optimizer.py:270)
+template <class V>
+__device__ __forceinline__ V sin_poly_v(V x) {
+  const V z = x * x;
+  V p = fmaf(z, 2.6303815071e-06f, splat<V>(-1.9821368161e-04f));
+  p = fmaf(p, z, splat<V>(8.3332318302e-03f));
+  p = fmaf(p, z, splat<V>(-1.6666665857e-01f));
+  return fmaf(x * z, p, x);
+}
 __device__ __forceinline__ void sin4(const float4 x, float& s0, float& s1, float& s2, float& s3) {
-  s0 = sin_poly(x.x); s1 = sin_poly(x.y); s2 = sin_poly(x.z); s3 = sin_poly(x.w);
+  const f2 a = sin_poly_v(f2(x.x, x.y)), b = sin_poly_v(f2(x.z, x.w));
+  s0 = a.v.x; s1 = a.v.y; s2 = b.v.x; s3 = b.v.y;
   const float mx = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));
   if (mx > 1.6f) { s0 = sin_slow(x.x); s1 = sin_slow(x.y); s2 = sin_slow(x.z); s3 = sin_slow(x.w); }
 }
@@ -133,17 +195,17 @@ __device__ inline void make_pass_const(const float* cam, const float* g, bool sp
 //   distort scale s, offset o = phi*uv, J_o = A I + Bc uv uv^T, ds/dk = sk, do/dk = psi*uv,
 //   undistort scale su, d(su uv)/duv = su I + Q uv uv^T, d(su uv)/dk = om*uv
 // ------------------------------------------------------------------------------------------
-template <int K>
+template <int K, class V = float>
 struct ModelScalars {
-  float s, phi, A, Bc, su, Q;
-  float sk[K > 0 ? K : 1], psi[K > 0 ? K : 1], om[K > 0 ? K : 1];
+  V s, phi, A, Bc, su, Q;
+  V sk[K > 0 ? K : 1], psi[K > 0 ? K : 1], om[K > 0 ? K : 1];
 };
 
 // Literal restatement of SimpleDivisional with its masked denominators (camera.py:829-942).
 // Used only when the cancellation-free closed form does not apply: k1 == 0 (trivial init, the
 // masked branches make ds/dk = 0 and J_o = 2/r^2 I - 8/r^4 uv uv^T) or
 // 1 - 4 k1 r^2 < 1e-6 (clamped square root).  Cold path.
-__device__ __noinline__ void divisional_literal(float k1, float r2, ModelScalars<1>& m) {
+__device__ __noinline__ void divisional_literal(float k1, float r2, ModelScalars<1, float>& m) {
   auto mf = [](float d) { return d == 0.f ? 1e6f : d; };
   const float x = 1.f - 4.f * k1 * r2;
   const float rad = 1.f - sqrtf(fmaxf(x, 0.f));
@@ -168,50 +230,63 @@ __device__ __noinline__ void divisional_literal(float k1, float r2, ModelScalars
   m.om[0] = -r2 / mf(dn * dn);
 }
 
-template <int MODEL>
-__device__ __forceinline__ void model_scalars(const PassConst& pc, float r2,
-                                              ModelScalars<num_dist(MODEL)>& m) {
-  if constexpr (MODEL == PINHOLE) {  // camera.py:532-562
-    m.s = 1.f; m.phi = 0.f; m.A = 0.f; m.Bc = 0.f; m.su = 1.f; m.Q = 0.f;
+// per-lane cold-path fix-up of the divisional scalars
+__device__ __forceinline__ void divisional_fixup(float k1, float r2, float x, ModelScalars<1, float>& m) {
+  if (k1 == 0.f || x < 1e-6f) divisional_literal(k1, r2, m);
+}
+__device__ __forceinline__ void divisional_fixup(float k1, f2 r2, f2 x, ModelScalars<1, f2>& m) {
+  if (k1 == 0.f || x.v.x < 1e-6f || x.v.y < 1e-6f) {
+    ModelScalars<1, float> a, b;
+    divisional_literal(k1, r2.v.x, a);
+    divisional_literal(k1, r2.v.y, b);
+    m.s = f2(a.s, b.s); m.phi = f2(a.phi, b.phi); m.A = f2(a.A, b.A); m.Bc = f2(a.Bc, b.Bc);
+    m.su = f2(a.su, b.su); m.Q = f2(a.Q, b.Q);
+    m.sk[0] = f2(a.sk[0], b.sk[0]); m.psi[0] = f2(a.psi[0], b.psi[0]); m.om[0] = f2(a.om[0], b.om[0]);
+  }
+}
+
+template <int MODEL, class V>
+__device__ __forceinline__ void model_scalars(const PassConst& pc, V r2, ModelScalars<num_dist(MODEL), V>& m) {
+  if constexpr (MODEL == PINHOLE) {  // camera.py:532-562 (never read: the K == 0 paths use constants)
+    m.s = splat<V>(1.f); m.phi = m.A = m.Bc = m.Q = splat<V>(0.f); m.su = splat<V>(1.f);
   } else if constexpr (MODEL == SIMPLE_RADIAL) {  // camera.py:611-660
-    m.s = fmaf(pc.k1, r2, 1.f);
-    m.phi = 2.f * pc.k1; m.A = m.phi; m.Bc = 0.f;
-    m.sk[0] = r2; m.psi[0] = 2.f;
-    m.su = fmaf(-pc.k1, r2, 1.f);
-    m.Q = -2.f * pc.k1;
+    m.s = fmaf(pc.k1, r2, splat<V>(1.f));
+    m.phi = splat<V>(2.f * pc.k1); m.A = m.phi; m.Bc = splat<V>(0.f);
+    m.sk[0] = r2; m.psi[0] = splat<V>(2.f);
+    m.su = fmaf(-pc.k1, r2, splat<V>(1.f));
+    m.Q = splat<V>(-2.f * pc.k1);
     m.om[0] = -r2;
   } else if constexpr (MODEL == RADIAL) {  // camera.py:712-786
-    const float r4 = r2 * r2;
-    m.s = fmaf(pc.k2, r4, fmaf(pc.k1, r2, 1.f));
-    m.phi = fmaf(4.f * pc.k2, r2, 2.f * pc.k1); m.A = m.phi; m.Bc = 8.f * pc.k2;
+    const V r4 = r2 * r2;
+    m.s = fmaf(pc.k2, r4, fmaf(pc.k1, r2, splat<V>(1.f)));
+    m.phi = fmaf(4.f * pc.k2, r2, splat<V>(2.f * pc.k1)); m.A = m.phi; m.Bc = splat<V>(8.f * pc.k2);
     m.sk[0] = r2; m.sk[1] = r4;
-    m.psi[0] = 2.f; m.psi[1] = 4.f * r2;
+    m.psi[0] = splat<V>(2.f); m.psi[1] = 4.f * r2;
     const float b1 = -pc.k1, b2 = fmaf(3.f * pc.k1, pc.k1, -pc.k2);
-    m.su = fmaf(b2, r4, fmaf(b1, r2, 1.f));
-    m.Q = fmaf(4.f * b2, r2, 2.f * b1);
+    m.su = fmaf(b2, r4, fmaf(b1, r2, splat<V>(1.f)));
+    m.Q = fmaf(4.f * b2, r2, splat<V>(2.f * b1));
     m.om[0] = fmaf(6.f * pc.k1, r4, -r2);
     m.om[1] = -r4;
   } else {  // SIMPLE_DIVISIONAL, camera.py:829-942
-    const float x = fmaf(-4.f * pc.k1, r2, 1.f);
-    if (pc.k1 == 0.f || x < 1e-6f) {
-      divisional_literal(pc.k1, r2, m);
-    } else {
-      // With t = sqrt(1 - 4 k1 r^2), w = 1 + t and 1 - t = 4 k1 r^2 / w every masked quotient of
-      // the reference collapses to a cancellation-free form that is finite at r^2 = 0:
-      //   s = 2/w, phi = A = 8 k1/(t w^2), Bc = 32 k1^2 (1+3t)/(t^3 w^3),
-      //   ds/dk = 4 r^2/(t w^2), psi = 4 (1 + 2t - t^2)/(t^3 w^2).
-      const float it = fast_rsqrt(x), t = x * it, w = 1.f + t, iw = fast_rcp(w);
-      const float itw2 = it * iw * iw, it2 = it * it;
-      m.s = 2.f * iw;
-      m.phi = 8.f * pc.k1 * itw2; m.A = m.phi;
-      m.Bc = 32.f * pc.k1 * pc.k1 * fmaf(3.f, t, 1.f) * itw2 * it2 * iw;
-      m.sk[0] = 4.f * r2 * itw2;
-      m.psi[0] = 4.f * fmaf(t, 2.f - t, 1.f) * itw2 * it2;
-      const float su = fast_rcp(fmaf(pc.k1, r2, 1.f));
-      m.su = su;
-      m.Q = -2.f * pc.k1 * su * su;
-      m.om[0] = -r2 * su * su;
-    }
+    // With t = sqrt(1 - 4 k1 r^2), w = 1 + t and 1 - t = 4 k1 r^2 / w every masked quotient of
+    // the reference collapses to a cancellation-free form that is finite at r^2 = 0:
+    //   s = 2/w, phi = A = 8 k1/(t w^2), Bc = 32 k1^2 (1+3t)/(t^3 w^3),
+    //   ds/dk = 4 r^2/(t w^2), psi = 4 (1 + 2t - t^2)/(t^3 w^2).
+    // The literal masked formulas (cold path) take over when k1 == 0 or the root is clamped.
+    const V x = fmaf(-4.f * pc.k1, r2, splat<V>(1.f));
+    const V xs = fmaxf(x, 1e-6f);
+    const V it = fast_rsqrt(xs), t = xs * it, w = 1.f + t, iw = fast_rcp(w);
+    const V itw2 = it * iw * iw, it2 = it * it;
+    m.s = 2.f * iw;
+    m.phi = (8.f * pc.k1) * itw2; m.A = m.phi;
+    m.Bc = (32.f * pc.k1 * pc.k1) * fmaf(3.f, t, splat<V>(1.f)) * itw2 * it2 * iw;
+    m.sk[0] = 4.f * r2 * itw2;
+    m.psi[0] = 4.f * fmaf(t, 2.f - t, splat<V>(1.f)) * itw2 * it2;
+    const V su = fast_rcp(fmaf(pc.k1, r2, splat<V>(1.f)));
+    m.su = su;
+    m.Q = (-2.f * pc.k1) * su * su;
+    m.om[0] = -(r2 * su * su);
+    divisional_fixup(pc.k1, r2, x, m);
   }
 }
 
@@ -223,45 +298,47 @@ __device__ __forceinline__ void model_scalars(const PassConst& pc, float r2,
 // ------------------------------------------------------------------------------------------
 struct FieldMask { bool up, lat, up_conf, lat_conf; };
 
-template <int MODEL, bool GEN_D, bool FULL>
-__device__ __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMask fm, float u,
-                                                 float v, float ox, float oy, float sin_olat, float cu,
-                                                 float cl, float inv_up2, float inv_lat2,
-                                                 float (&acc)[Dims<MODEL>::NACC]) {
+template <int MODEL, bool GEN_D, bool FULL, class V>
+__device__ __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMask fm, V u,
+                                                 float v, V ox, V oy, V sin_olat, V cu,
+                                                 V cl, float inv_up2, float inv_lat2,
+                                                 V (&acc)[Dims<MODEL>::NACC]) {
   constexpr int K = Dims<MODEL>::K, NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH;
   const bool has_up = FULL || fm.up, has_lat = FULL || fm.lat;
-  const float r2 = fmaf(u, u, v * v);
-  ModelScalars<K> m;
-  model_scalars<MODEL>(pc, r2, m);
+  const V r2 = fmaf(u, u, splat<V>(v * v));
+  ModelScalars<K, V> m;
+  model_scalars<MODEL, V>(pc, r2, m);
 
-  float su_[NF], sl_[NF];  // Jacobian row scalars (up: along n_perp; latitude)
-  float e = 0.f, w_up = 0.f, r_lat = 0.f, w_lat = 0.f;
-  float dx = 0.f, dy = 0.f, uvd = 0.f;
-  if constexpr (GEN_D) { dx = -u * pc.dsx; dy = -v * pc.dsy; uvd = fmaf(u, dx, v * dy); }
+  V su_[NF], sl_[NF];  // Jacobian row scalars (up: along n_perp; latitude)
+  V e = splat<V>(0.f), w_up = e, r_lat = e, w_lat = e;
+  V dx = e, uvd = e;
+  float dy = 0.f;
+  if constexpr (GEN_D) { dx = -(u * pc.dsx); dy = -v * pc.dsy; uvd = fmaf(u, dx, splat<V>(v * dy)); }
 
   if (has_up) {  // ---- up field: perspective_fields.py:47-182 ----
-    const float p0x = fmaf(-pc.c, u, pc.a), p0y = fmaf(-pc.c, v, pc.b);
-    float px = p0x, py = p0y, iota = 0.f;
+    const V p0x = fmaf(-pc.c, u, splat<V>(pc.a));
+    const float p0y = fmaf(-pc.c, v, pc.b);
+    V px = p0x, py = splat<V>(p0y), iota = splat<V>(0.f);
     if constexpr (K > 0) {
-      iota = fmaf(u, p0x, v * p0y);
-      const float pi = m.phi * iota;
+      iota = fmaf(u, p0x, splat<V>(v * p0y));
+      const V pi = m.phi * iota;
       px = fmaf(m.s, p0x, pi * u);
-      py = fmaf(m.s, p0y, pi * v);
+      py = fmaf(m.s, splat<V>(p0y), pi * v);
     }
-    const float rho2 = fmaf(px, px, py * py);
-    const float irho = fast_rsqrt(fmaxf(rho2, 1e-24f));  // F.normalize eps (perspective_fields.py:79)
-    const float upx = px * irho, upy = py * irho;
-    const float q = irho * irho;
-    const float Ap = -py * q, Bp = px * q;  // (n_perp . z)/rho = Ap z_x + Bp z_y
-    const float Nu = fmaf(Ap, u, Bp * v);
+    const V rho2 = fmaf(px, px, py * py);
+    const V irho = fast_rsqrt(fmaxf(rho2, 1e-24f));  // F.normalize eps (perspective_fields.py:79)
+    const V upx = px * irho, upy = py * irho;
+    const V q = irho * irho;
+    const V Ap = -(py * q), Bp = px * q;  // (n_perp . z)/rho = Ap z_x + Bp z_y
+    const V Nu = fmaf(Ap, u, Bp * v);
     // residual (lm_optimizer.py:266) and its component along n_perp
-    const float rx = ox - upx, ry = oy - upy;
-    e = fmaf(upx, oy, -upy * ox);
-    const float chi = fmaf(rx, rx, ry * ry) * inv_up2;
+    const V rx = ox - upx, ry = oy - upy;
+    e = fmaf(upx, oy, -(upy * ox));
+    const V chi = fmaf(rx, rx, ry * ry) * inv_up2;
     // Huber (lm_optimizer.py:79-87): chi + 1e-8 == chi in fp32 for chi > 1
-    const float mm = fmaxf(chi, 1.f);
-    const float isx = fast_rsqrt(mm);
-    const float cost = fminf(chi, 1.f) * fmaf(2.f * mm, isx, -1.f);
+    const V mm = fmaxf(chi, 1.f);
+    const V isx = fast_rsqrt(mm);
+    const V cost = fminf(chi, 1.f) * fmaf(2.f * mm, isx, splat<V>(-1.f));
     w_up = isx * cu;
     acc[NH + NF] = fmaf(cost, cu, acc[NH + NF]);
     // gravity columns: M z_j, z_j = (T0j - u T2j, T1j - v T2j)
@@ -269,9 +346,11 @@ __device__ __forceinline__ void pixel_accumulate(const PassConst& pc, const Fiel
       su_[0] = fmaf(Ap, pc.T00, fmaf(Bp, pc.T10, -pc.T20 * Nu));
       su_[1] = fmaf(Ap, pc.T01, fmaf(Bp, pc.T11, -pc.T21 * Nu));
     } else {
-      const float z0x = fmaf(-u, pc.T20, pc.T00), z0y = fmaf(-v, pc.T20, pc.T10);
-      const float z1x = fmaf(-u, pc.T21, pc.T01), z1y = fmaf(-v, pc.T21, pc.T11);
-      const float pn = m.phi * Nu;
+      const V z0x = fmaf(u, -pc.T20, splat<V>(pc.T00));
+      const float z0y = fmaf(-v, pc.T20, pc.T10);
+      const V z1x = fmaf(u, -pc.T21, splat<V>(pc.T01));
+      const float z1y = fmaf(-v, pc.T21, pc.T11);
+      const V pn = m.phi * Nu;
       su_[0] = fmaf(m.s, fmaf(Ap, z0x, Bp * z0y), pn * fmaf(u, z0x, v * z0y));
       su_[1] = fmaf(m.s, fmaf(Ap, z1x, Bp * z1y), pn * fmaf(u, z1x, v * z1y));
     }
@@ -280,66 +359,66 @@ __device__ __forceinline__ void pixel_accumulate(const PassConst& pc, const Fiel
       if constexpr (K == 0) {
         su_[2] = pc.c * Nu;
       } else {
-        const float Np0 = fmaf(Ap, p0x, Bp * p0y);
-        const float t = fmaf(pc.c, fmaf(m.phi, r2, m.s), -iota * (fmaf(m.Bc, r2, m.A) + m.phi));
-        su_[2] = fmaf(Nu, t, -m.phi * r2 * Np0);
+        const V Np0 = fmaf(Ap, p0x, Bp * p0y);
+        const V t = fmaf(pc.c, fmaf(m.phi, r2, m.s), -(iota * (fmaf(m.Bc, r2, m.A) + m.phi)));
+        su_[2] = fmaf(Nu, t, -(m.phi * r2 * Np0));
       }
     } else {
-      const float Nd = fmaf(Ap, dx, Bp * dy);
+      const V Nd = fmaf(Ap, dx, Bp * dy);
       if constexpr (K == 0) {
         su_[2] = -pc.c * Nd;
       } else {
-        const float Np0 = fmaf(Ap, p0x, Bp * p0y);
-        const float p0d = fmaf(p0x, dx, p0y * dy);
-        const float t = fmaf(iota * m.Bc, uvd, m.phi * (p0d - pc.c * uvd));
+        const V Np0 = fmaf(Ap, p0x, Bp * p0y);
+        const V p0d = fmaf(p0x, dx, splat<V>(p0y * dy));
+        const V t = fmaf(iota * m.Bc, uvd, m.phi * (p0d - pc.c * uvd));
         su_[2] = fmaf(fmaf(iota, m.A, -pc.c * m.s), Nd, fmaf(m.phi * uvd, Np0, Nu * t));
       }
     }
     if constexpr (K > 0) {
-      const float Np0 = fmaf(Ap, p0x, Bp * p0y);
-      const float iN = iota * Nu;
+      const V Np0 = fmaf(Ap, p0x, Bp * p0y);
+      const V iN = iota * Nu;
 #pragma unroll
       for (int k = 0; k < K; k++) su_[3 + k] = fmaf(m.sk[k], Np0, m.psi[k] * iN);
     }
   }
 
   if (has_lat) {  // ---- latitude field: perspective_fields.py:185-275 ----
-    const float S = fmaf(pc.a, u, pc.b * v);
-    float m2, ln;
+    const V S = fmaf(pc.a, u, splat<V>(pc.b * v));
+    V m2, ln;
     if constexpr (K == 0) { m2 = r2 + 1.f; ln = S + pc.c; }
-    else { m2 = fmaf(m.su * m.su, r2, 1.f); ln = fmaf(m.su, S, pc.c); }
-    const float im = fast_rsqrt(m2);
-    const float l = ln * im;
-    const float lc = fminf(fmaxf(l, -1.f + 1e-6f), 1.f - 1e-6f);
+    else { m2 = fmaf(m.su * m.su, r2, splat<V>(1.f)); ln = fmaf(m.su, S, splat<V>(pc.c)); }
+    const V im = fast_rsqrt(m2);
+    const V l = ln * im;
+    const V lc = fminf(fmaxf(l, -1.f + 1e-6f), 1.f - 1e-6f);
     r_lat = sin_olat - lc;  // lm_optimizer.py:270-271
-    const float chi = r_lat * r_lat * inv_lat2;
-    const float mm = fmaxf(chi, 1.f);
-    const float isx = fast_rsqrt(mm);
-    const float cost = fminf(chi, 1.f) * fmaf(2.f * mm, isx, -1.f);
+    const V chi = r_lat * r_lat * inv_lat2;
+    const V mm = fmaxf(chi, 1.f);
+    const V isx = fast_rsqrt(mm);
+    const V cost = fminf(chi, 1.f) * fmaf(2.f * mm, isx, splat<V>(-1.f));
     w_lat = isx * cl;
     acc[NH + NF + 1] = fmaf(cost, cl, acc[NH + NF + 1]);
     if constexpr (K == 0) {
-      sl_[0] = im * fmaf(pc.T00, u, fmaf(pc.T10, v, pc.T20));
-      sl_[1] = im * fmaf(pc.T01, u, fmaf(pc.T11, v, pc.T21));
+      sl_[0] = im * fmaf(pc.T00, u, splat<V>(fmaf(pc.T10, v, pc.T20)));
+      sl_[1] = im * fmaf(pc.T01, u, splat<V>(fmaf(pc.T11, v, pc.T21)));
     } else {
-      sl_[0] = im * fmaf(m.su, fmaf(pc.T00, u, pc.T10 * v), pc.T20);
-      sl_[1] = im * fmaf(m.su, fmaf(pc.T01, u, pc.T11 * v), pc.T21);
+      sl_[0] = im * fmaf(m.su, fmaf(pc.T00, u, splat<V>(pc.T10 * v)), splat<V>(pc.T20));
+      sl_[1] = im * fmaf(m.su, fmaf(pc.T01, u, splat<V>(pc.T11 * v)), splat<V>(pc.T21));
     }
-    const float li = l * im;
+    const V li = l * im;
     if constexpr (!GEN_D) {
       if constexpr (K == 0) {
-        sl_[2] = im * fmaf(-l, im, pc.c);  // = -gamma.uv with r^2 = m^2 - 1
+        sl_[2] = im * fmaf(-l, im, splat<V>(pc.c));  // = -gamma.uv with r^2 = m^2 - 1
       } else {
-        const float guv = im * fmaf(-li * m.su, r2, S);
-        sl_[2] = -fmaf(m.Q, r2, m.su) * guv;
+        const V guv = im * fmaf(-(li * m.su), r2, S);
+        sl_[2] = -(fmaf(m.Q, r2, m.su) * guv);
 #pragma unroll
         for (int k = 0; k < K; k++) sl_[3 + k] = m.om[k] * guv;
       }
     } else {
-      const float U = m.su * u, V = m.su * v;
-      const float gx = fmaf(-U, li, pc.a) * im, gy = fmaf(-V, li, pc.b) * im;
-      const float gd = fmaf(gx, dx, gy * dy);
-      const float guv = fmaf(gx, u, gy * v);
+      const V U = m.su * u, Vv = m.su * v;
+      const V gx = fmaf(-U, li, splat<V>(pc.a)) * im, gy = fmaf(-Vv, li, splat<V>(pc.b)) * im;
+      const V gd = fmaf(gx, dx, gy * dy);
+      const V guv = fmaf(gx, u, gy * v);
       sl_[2] = fmaf(m.su, gd, m.Q * uvd * guv);
       if constexpr (K > 0) {
 #pragma unroll
@@ -349,18 +428,18 @@ __device__ __forceinline__ void pixel_accumulate(const PassConst& pc, const Fiel
   }
 
   // ---- J^T W J, J^T W r (lm_optimizer.py:346-359) ----
-  float wu[NF], wl[NF];
+  V wu[NF], wl[NF];
 #pragma unroll
   for (int i = 0; i < NF; i++) {
-    wu[i] = has_up ? w_up * su_[i] : 0.f;
-    wl[i] = has_lat ? w_lat * sl_[i] : 0.f;
+    wu[i] = has_up ? w_up * su_[i] : splat<V>(0.f);
+    wl[i] = has_lat ? w_lat * sl_[i] : splat<V>(0.f);
   }
   int idx = 0;
 #pragma unroll
   for (int i = 0; i < NF; i++) {
 #pragma unroll
     for (int j = i; j < NF; j++) {
-      float h = acc[idx];
+      V h = acc[idx];
       if (has_up) h = fmaf(wu[i], su_[j], h);
       if (has_lat) h = fmaf(wl[i], sl_[j], h);
       acc[idx++] = h;
@@ -368,7 +447,7 @@ __device__ __forceinline__ void pixel_accumulate(const PassConst& pc, const Fiel
   }
 #pragma unroll
   for (int i = 0; i < NF; i++) {
-    float g = acc[NH + i];
+    V g = acc[NH + i];
     if (has_up) g = fmaf(wu[i], e, g);
     if (has_lat) g = fmaf(wl[i], r_lat, g);
     acc[NH + i] = g;

@@ -19,6 +19,7 @@
 #include <dlfcn.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -402,9 +403,23 @@ __global__ void shared_stop_kernel(const PassArgs a, const float* sum_in) {
 // ---------------------------------------------------------------------------------------------
 // the fused pass kernel
 // ---------------------------------------------------------------------------------------------
-template <int MODEL, bool GEN_D, bool FULL>
-__global__ void __launch_bounds__(MAX_WARPS * 32) lm_pass_kernel(const PassArgs a) {
+// Register / occupancy budget per instantiation.  Two resident CTAs per SM everywhere, so that one
+// CTA's prologue / reduction / solver epilogue overlaps the other's streaming loop:
+//   pinhole            : CTAs of <= 10 warps, <= 102 registers (96 used)
+//   distortion models  : packed accumulators need ~168 registers -> CTAs of <= 6 warps
+template <int MODEL, bool PACK>
+struct Tune {
+  static constexpr int MAX_WARPS_CTA = (MODEL == PINHOLE || !PACK) ? MAX_WARPS : 6;
+  static constexpr int MIN_BLOCKS = 2;
+  static constexpr int UNROLL = 2;
+};
+inline int max_warps_for(int model, bool pack) { return (model == PINHOLE || !pack) ? MAX_WARPS : 6; }
+
+template <int MODEL, bool GEN_D, bool FULL, bool PACK>
+__global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MODEL, PACK>::MIN_BLOCKS)
+    lm_pass_kernel(const PassArgs a) {
   constexpr int NACC = Dims<MODEL>::NACC;
+  using V = typename std::conditional<PACK, f2, float>::type;  // 2 pixels per op when packed
   const int b = blockIdx.x / a.tiles_per_image;
   const int tile = blockIdx.x - b * a.tiles_per_image;
   if (!a.is_final) {
@@ -434,9 +449,9 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) lm_pass_kernel(const PassArgs 
   const int yt1 = min(H, yt0 + a.rows_per_tile);
   const int RJ = (a.rows_per_tile + a.rsub - 1) / a.rsub;
 
-  float acc[NACC];
+  V acc[NACC];
 #pragma unroll
-  for (int i = 0; i < NACC; i++) acc[i] = 0.f;
+  for (int i = 0; i < NACC; i++) acc[i] = splat<V>(0.f);
 
   for (int job = warp; job < NS * a.rsub; job += nwarps) {
     const int strip = job % NS, sub = job / NS;
@@ -451,7 +466,7 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) lm_pass_kernel(const PassArgs 
     const float* p_lat = (FULL || fm.lat) ? a.lat + (size_t)b * N + off : nullptr;
     const float* p_cu = (FULL || fm.up_conf) ? a.uconf + (size_t)b * N + off : nullptr;
     const float* p_cl = (FULL || fm.lat_conf) ? a.lconf + (size_t)b * N + off : nullptr;
-#pragma unroll 2
+#pragma unroll(Tune<MODEL, PACK>::UNROLL)
     for (int y = y0; y < y1; ++y) {
       float4 ox = make_float4(0.f, 0.f, 0.f, 0.f), oy = ox, ol = ox;
       float4 cu = make_float4(1.f, 1.f, 1.f, 1.f), cl = cu;
@@ -462,17 +477,24 @@ __global__ void __launch_bounds__(MAX_WARPS * 32) lm_pass_kernel(const PassArgs 
       const float v = ((float)y - pc.cy) * pc.inv_fy;
       float sl0 = 0.f, sl1 = 0.f, sl2 = 0.f, sl3 = 0.f;
       if (FULL || fm.lat) sin4(ol, sl0, sl1, sl2, sl3);
-      pixel_accumulate<MODEL, GEN_D, FULL>(pc, fm, u[0], v, ox.x, oy.x, sl0, cu.x, cl.x, inv_up2, inv_lat2, acc);
-      pixel_accumulate<MODEL, GEN_D, FULL>(pc, fm, u[1], v, ox.y, oy.y, sl1, cu.y, cl.y, inv_up2, inv_lat2, acc);
-      pixel_accumulate<MODEL, GEN_D, FULL>(pc, fm, u[2], v, ox.z, oy.z, sl2, cu.z, cl.z, inv_up2, inv_lat2, acc);
-      pixel_accumulate<MODEL, GEN_D, FULL>(pc, fm, u[3], v, ox.w, oy.w, sl3, cu.w, cl.w, inv_up2, inv_lat2, acc);
+      if constexpr (PACK) {
+        pixel_accumulate<MODEL, GEN_D, FULL, f2>(pc, fm, f2(u[0], u[1]), v, f2(ox.x, ox.y), f2(oy.x, oy.y),
+                                                 f2(sl0, sl1), f2(cu.x, cu.y), f2(cl.x, cl.y), inv_up2, inv_lat2, acc);
+        pixel_accumulate<MODEL, GEN_D, FULL, f2>(pc, fm, f2(u[2], u[3]), v, f2(ox.z, ox.w), f2(oy.z, oy.w),
+                                                 f2(sl2, sl3), f2(cu.z, cu.w), f2(cl.z, cl.w), inv_up2, inv_lat2, acc);
+      } else {
+        pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[0], v, ox.x, oy.x, sl0, cu.x, cl.x, inv_up2, inv_lat2, acc);
+        pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[1], v, ox.y, oy.y, sl1, cu.y, cl.y, inv_up2, inv_lat2, acc);
+        pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[2], v, ox.z, oy.z, sl2, cu.z, cl.z, inv_up2, inv_lat2, acc);
+        pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[3], v, ox.w, oy.w, sl3, cu.w, cl.w, inv_up2, inv_lat2, acc);
+      }
     }
   }
 
   // ---- CTA reduction: shuffle tree, then fixed-order sum over warps ----
 #pragma unroll
   for (int i = 0; i < NACC; i++) {
-    float x = acc[i];
+    float x = hsum(acc[i]);
     x += __shfl_xor_sync(0xffffffffu, x, 16);
     x += __shfl_xor_sync(0xffffffffu, x, 8);
     x += __shfl_xor_sync(0xffffffffu, x, 4);
@@ -570,8 +592,8 @@ __global__ void render_kernel(int B, int H, int W, const float* cam, const float
   pc.k1 = c[6]; pc.k2 = c[7]; pc.a = g[0]; pc.b = g[1]; pc.c = g[2];
   const float u = ((float)x - pc.cx) / c[2], v = ((float)y - pc.cy) / c[3];
   const float r2 = u * u + v * v;
-  ModelScalars<num_dist(MODEL)> m;
-  model_scalars<MODEL>(pc, r2, m);
+  ModelScalars<num_dist(MODEL), float> m;
+  model_scalars<MODEL, float>(pc, r2, m);
   const float p0x = g[0] - g[2] * u, p0y = g[1] - g[2] * v;
   const float iota = u * p0x + v * p0y;
   float px = m.s * p0x + m.phi * iota * u, py = m.s * p0y + m.phi * iota * v;
@@ -678,11 +700,14 @@ struct Layout {  // carve the scratch buffer
 
 struct TileCfg { int nwarps, rsub, rows_per_tile, tiles_per_image; };
 
-TileCfg tile_config(int B, int H, int W, int num_sms, int rows_override) {
+TileCfg tile_config(int B, int H, int W, int num_sms, int rows_override, int max_warps) {
   TileCfg t;
-  const int NS = (W + 127) / 128;
-  if (NS <= MAX_WARPS) { t.rsub = std::max(1, MAX_WARPS / NS); t.nwarps = NS * t.rsub; }
-  else { t.rsub = 1; t.nwarps = 8; }
+  const int NS = (W + 127) / 128;  // 128-pixel column strips, one warp each
+  if (NS <= max_warps) { t.rsub = std::max(1, max_warps / NS); t.nwarps = NS * t.rsub; }
+  else {  // more strips than warps: every warp walks NS / nwarps strips (nwarps divides NS)
+    t.rsub = 1; t.nwarps = 1;
+    for (int d = 1; d <= max_warps; d++) if (NS % d == 0) t.nwarps = d;
+  }
   int rj = 48;  // rows walked by one warp per tile
   if (rows_override > 0) rj = std::max(1, rows_override / t.rsub);
   else
@@ -721,28 +746,43 @@ int ensure_scratch(gclm_handle* h, size_t bytes) {
 }
 
 int max_tiles_for(int H, int W) {
-  const int NS = (W + 127) / 128;
-  const int rsub = NS <= MAX_WARPS ? std::max(1, MAX_WARPS / NS) : 1;
-  return (H + 4 * rsub - 1) / (4 * rsub) + 1;  // smallest auto tile is 4 rows per warp
+  (void)W;
+  return (H + 3) / 4 + 1;  // smallest auto tile is 4 rows (rsub == 1)
 }
 
-template <int MODEL>
+template <int MODEL, bool PACK>
 void launch_pass_model(const PassArgs& a, bool gen_d, bool full, dim3 grid, dim3 block, cudaStream_t s) {
   if (gen_d) {
-    if (full) lm_pass_kernel<MODEL, true, true><<<grid, block, 0, s>>>(a);
-    else lm_pass_kernel<MODEL, true, false><<<grid, block, 0, s>>>(a);
+    if (full) lm_pass_kernel<MODEL, true, true, PACK><<<grid, block, 0, s>>>(a);
+    else lm_pass_kernel<MODEL, true, false, PACK><<<grid, block, 0, s>>>(a);
   } else {
-    if (full) lm_pass_kernel<MODEL, false, true><<<grid, block, 0, s>>>(a);
-    else lm_pass_kernel<MODEL, false, false><<<grid, block, 0, s>>>(a);
+    if (full) lm_pass_kernel<MODEL, false, true, PACK><<<grid, block, 0, s>>>(a);
+    else lm_pass_kernel<MODEL, false, false, PACK><<<grid, block, 0, s>>>(a);
   }
 }
 
+// GCLM_PACK=0 selects the scalar (one pixel per instruction) build of the pass kernel: A/B knob.
+bool use_packed() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GCLM_PACK"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v != 0;
+}
+
 void launch_pass(const PassArgs& a, bool gen_d, bool full, dim3 grid, dim3 block, cudaStream_t s) {
-  switch (a.model) {
-    case PINHOLE: launch_pass_model<PINHOLE>(a, gen_d, full, grid, block, s); break;
-    case SIMPLE_RADIAL: launch_pass_model<SIMPLE_RADIAL>(a, gen_d, full, grid, block, s); break;
-    case RADIAL: launch_pass_model<RADIAL>(a, gen_d, full, grid, block, s); break;
-    default: launch_pass_model<SIMPLE_DIVISIONAL>(a, gen_d, full, grid, block, s); break;
+  if (use_packed()) {
+    switch (a.model) {
+      case PINHOLE: launch_pass_model<PINHOLE, true>(a, gen_d, full, grid, block, s); break;
+      case SIMPLE_RADIAL: launch_pass_model<SIMPLE_RADIAL, true>(a, gen_d, full, grid, block, s); break;
+      case RADIAL: launch_pass_model<RADIAL, true>(a, gen_d, full, grid, block, s); break;
+      default: launch_pass_model<SIMPLE_DIVISIONAL, true>(a, gen_d, full, grid, block, s); break;
+    }
+  } else {
+    switch (a.model) {
+      case PINHOLE: launch_pass_model<PINHOLE, false>(a, gen_d, full, grid, block, s); break;
+      case SIMPLE_RADIAL: launch_pass_model<SIMPLE_RADIAL, false>(a, gen_d, full, grid, block, s); break;
+      case RADIAL: launch_pass_model<RADIAL, false>(a, gen_d, full, grid, block, s); break;
+      default: launch_pass_model<SIMPLE_DIVISIONAL, false>(a, gen_d, full, grid, block, s); break;
+    }
   }
 }
 
@@ -874,7 +914,8 @@ int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt
   if (prob->shared_intrinsics) return GCLM_ERR_INVALID_ARGUMENT;
   CUDA_TRY(h, cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-  const TileCfg t = tile_config(prob->batch, prob->height, prob->width, h->num_sms, opt->rows_per_tile);
+  const TileCfg t = tile_config(prob->batch, prob->height, prob->width, h->num_sms, opt->rows_per_tile,
+                                max_warps_for(prob->camera_model, use_packed()));
   const Layout L = make_layout(prob->batch, std::max(t.tiles_per_image, max_tiles_for(prob->height, prob->width)));
   st = ensure_scratch(h, L.total);
   if (st != GCLM_OK) return st;
@@ -908,7 +949,8 @@ int gclm_solve_shared(gclm_handle* h, const gclm_problem* prob, const gclm_optio
   }
   CUDA_TRY(h, cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-  const TileCfg t = tile_config(prob->batch, prob->height, prob->width, h->num_sms, opt->rows_per_tile);
+  const TileCfg t = tile_config(prob->batch, prob->height, prob->width, h->num_sms, opt->rows_per_tile,
+                                max_warps_for(prob->camera_model, use_packed()));
   const Layout L = make_layout(prob->batch, std::max(t.tiles_per_image, max_tiles_for(prob->height, prob->width)));
   st = ensure_scratch(h, L.total);
   if (st != GCLM_OK) return st;
