@@ -237,6 +237,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--e2e-chunk", type=int, default=128)
+    ap.add_argument("--rows-per-tile", type=int, default=0, help="engine tiling knob (0 = auto)")
+    ap.add_argument("--no-check", action="store_true", help="skip the calibration sanity check (experiments)")
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])
     if args.batch > 0:
@@ -269,7 +271,8 @@ def main():
         cam_gt[:, 2:4] = gt_params(model, 1, h, w, 4321)[0][0, 3]
     fields = eng.render_fields(model, torch.from_numpy(cam_gt).to(dev), torch.from_numpy(grav_gt).to(dev), h, w,
                                sigma=0.02, conf_lo=0.2, seed=1234 + rank)
-    opt = G.LMOptimizer({"camera_model": model, "num_steps": iters, "early_stop": False}).eval()
+    opt = G.LMOptimizer({"camera_model": model, "num_steps": iters, "early_stop": False,
+                         "rows_per_tile": args.rows_per_tile}).eval()
     opt.shared_intrinsics = shared
     if shared and world > 1:
         from geocalib_b200.parallel import make_comm
@@ -316,7 +319,7 @@ def main():
 
     # parity guard on the timed output: recovered focal close to the synthetic ground truth
     f_err = float((out["camera"]._data[:, 3].cpu() / torch.from_numpy(cam_gt[:, 3]) - 1).abs().median())
-    assert f_err < 0.05, f"median focal error {f_err}: the timed run did not calibrate"
+    assert args.no_check or f_err < 0.05, f"median focal error {f_err}: the timed run did not calibrate"
 
     # ---- roofline of the fused pass kernel ----
     passes = iters + 1

@@ -13,7 +13,10 @@ from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_int64, c_uint64
 from pathlib import Path
 
 CSRC = Path(__file__).resolve().parent / "csrc"
-LIB_PATH = CSRC / "libgclm.so"
+import os as _os
+
+# GCLM_LIB=<path> loads an alternative build of the same ABI (A/B experiments in tools/)
+LIB_PATH = Path(_os.environ["GCLM_LIB"]) if _os.environ.get("GCLM_LIB") else CSRC / "libgclm.so"
 
 GCLM_OK = 0
 STOP_BATCH, STOP_PER_IMAGE = 0, 1

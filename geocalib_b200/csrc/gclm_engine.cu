@@ -37,6 +37,10 @@ namespace gclm {
 constexpr int PSTRIDE = 12;  // cam[8] + g[3] + pad
 constexpr unsigned FLAG_FROZEN = 0x100u;
 constexpr int MAX_WARPS = 10;
+#ifndef GCLM_RING_STAGES
+#define GCLM_RING_STAGES 4
+#endif
+constexpr int RING_STAGES = GCLM_RING_STAGES;  // rows prefetched per lane by the cp.async ring
 // shared-intrinsics Schur partials per image (floats):
 //   [0,9) C  [9,18) E^T D~^-1 E  [18,21) g_c  [21,24) E^T D~^-1 g_g  [24] not-converged flag
 //   [25,31) W = D~^-1 E (2 x ni)  [31,33) wg = D~^-1 g_g
@@ -79,6 +83,16 @@ __device__ __forceinline__ float4 ldg_stream(const float* p) {
   asm volatile("ld.global.nc.L1::no_allocate.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];"
                : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
                : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void cp_async16(unsigned dst_smem, const float* src) {
+  asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ float4 lds128(unsigned addr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
   return r;
 }
 
@@ -326,7 +340,7 @@ __device__ __noinline__ void schur_image(const PassArgs& a, int b, const float* 
 }
 
 // Sum the per-image Schur partials of this rank in a fixed order -> sum_out[SCHUR_NSUM].
-__global__ void __launch_bounds__(1024) shared_reduce_kernel(const PassArgs a, float* sum_out) {
+__global__ void __launch_bounds__(1024) shared_reduce_kernel(const __grid_constant__ PassArgs a, float* sum_out) {
   __shared__ float s[32][SCHUR_NSUM];
   if (*(volatile int*)&a.ctrl->stop) return;
   const int j = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -345,7 +359,7 @@ __global__ void __launch_bounds__(1024) shared_reduce_kernel(const PassArgs a, f
 
 // Every image redundantly solves the tiny Schur system and applies its own update.
 template <int MODEL>
-__global__ void shared_update_kernel(const PassArgs a, const float* sum_in) {
+__global__ void shared_update_kernel(const __grid_constant__ PassArgs a, const float* sum_in) {
   constexpr int K = Dims<MODEL>::K;
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (*(volatile int*)&a.ctrl->stop) return;
@@ -417,7 +431,7 @@ inline int max_warps_for(int model, bool pack) { return (model == PINHOLE || !pa
 
 template <int MODEL, bool GEN_D, bool FULL, bool PACK>
 __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MODEL, PACK>::MIN_BLOCKS)
-    lm_pass_kernel(const PassArgs a) {
+    lm_pass_kernel(const __grid_constant__ PassArgs a) {
   constexpr int NACC = Dims<MODEL>::NACC;
   using V = typename std::conditional<PACK, f2, float>::type;  // 2 pixels per op when packed
   const int b = blockIdx.x / a.tiles_per_image;
@@ -441,6 +455,8 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
   const FieldMask fm = {a.up != nullptr, a.lat != nullptr, a.uconf != nullptr, a.lconf != nullptr};
   const float inv_up2 = 1.f / (a.up_scale * a.up_scale), inv_lat2 = 1.f / (a.lat_scale * a.lat_scale);
 
+  extern __shared__ __align__(16) unsigned char dyn_smem[];
+  const unsigned smem_u32 = (unsigned)__cvta_generic_to_shared(dyn_smem);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int W = a.W, H = a.H;
   const size_t N = (size_t)H * W;
@@ -466,14 +482,12 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
     const float* p_lat = (FULL || fm.lat) ? a.lat + (size_t)b * N + off : nullptr;
     const float* p_cu = (FULL || fm.up_conf) ? a.uconf + (size_t)b * N + off : nullptr;
     const float* p_cl = (FULL || fm.lat_conf) ? a.lconf + (size_t)b * N + off : nullptr;
-#pragma unroll(Tune<MODEL, PACK>::UNROLL)
-    for (int y = y0; y < y1; ++y) {
-      float4 ox = make_float4(0.f, 0.f, 0.f, 0.f), oy = ox, ol = ox;
-      float4 cu = make_float4(1.f, 1.f, 1.f, 1.f), cl = cu;
-      if (FULL || fm.up) { ox = ldg_stream(p_ux); oy = ldg_stream(p_ux + N); p_ux += W; }
-      if (FULL || fm.lat) { ol = ldg_stream(p_lat); p_lat += W; }
-      if (FULL || fm.up_conf) { cu = ldg_stream(p_cu); p_cu += W; }
-      if (FULL || fm.lat_conf) { cl = ldg_stream(p_cl); p_cl += W; }
+    auto row = [&](const float4 ox, const float4 oy, const float4 ol, const float4 cu, const float4 cl, int y) {
+#ifdef GCLM_NOCOMPUTE  // experiment: pure streaming ceiling of this access pattern
+      acc[0] = acc[0] + splat<V>(ox.x + ox.y + ox.z + ox.w + oy.x + oy.y + oy.z + oy.w + ol.x + ol.y + ol.z + ol.w +
+                                 cu.x + cu.y + cu.z + cu.w + cl.x + cl.y + cl.z + cl.w + (float)y);
+      return;
+#endif
       const float v = ((float)y - pc.cy) * pc.inv_fy;
       float sl0 = 0.f, sl1 = 0.f, sl2 = 0.f, sl3 = 0.f;
       if (FULL || fm.lat) sin4(ol, sl0, sl1, sl2, sl3);
@@ -487,6 +501,50 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
         pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[1], v, ox.y, oy.y, sl1, cu.y, cl.y, inv_up2, inv_lat2, acc);
         pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[2], v, ox.z, oy.z, sl2, cu.z, cl.z, inv_up2, inv_lat2, acc);
         pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[3], v, ox.w, oy.w, sl3, cu.w, cl.w, inv_up2, inv_lat2, acc);
+      }
+    };
+    if constexpr (FULL && RING_STAGES > 0) {
+      // ---- cp.async (LDGSTS) ring: every lane prefetches ITS float4 of each of the 5 planes
+      // STAGES rows ahead into a private shared-memory slot (no barriers: a lane only ever reads
+      // what it copied), so STAGES - 1 rows of loads are in flight while a row is computed and no
+      // registers are held across the HBM latency.
+      const unsigned plane_stride = blockDim.x * 16u, stage_stride = 5u * plane_stride;
+      const unsigned slot0 = smem_u32 + threadIdx.x * 16u;  // [stage][plane][thread] x 16 B
+      const unsigned slot_end = slot0 + (unsigned)RING_STAGES * stage_stride;
+      auto issue = [&](unsigned d) {
+        cp_async16(d, p_ux); cp_async16(d + plane_stride, p_ux + N);
+        cp_async16(d + 2u * plane_stride, p_lat);
+        cp_async16(d + 3u * plane_stride, p_cu); cp_async16(d + 4u * plane_stride, p_cl);
+        p_ux += W; p_lat += W; p_cu += W; p_cl += W;
+      };
+#pragma unroll
+      for (int st = 0; st < RING_STAGES; st++) {
+        if (y0 + st < y1) issue(slot0 + st * stage_stride);
+        cp_async_commit();
+      }
+      unsigned d = slot0;
+#pragma unroll 1
+      for (int y = y0; y < y1; ++y) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(RING_STAGES > 0 ? RING_STAGES - 1 : 0) : "memory");
+        const float4 ox = lds128(d), oy = lds128(d + plane_stride), ol = lds128(d + 2u * plane_stride);
+        const float4 cu = lds128(d + 3u * plane_stride), cl = lds128(d + 4u * plane_stride);
+        row(ox, oy, ol, cu, cl, y);
+        if (y + RING_STAGES < y1) issue(d);  // refill the slot just consumed (after its values were used)
+        cp_async_commit();
+        d += stage_stride;
+        if (d == slot_end) d = slot0;
+      }
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+    } else {
+#pragma unroll(Tune<MODEL, PACK>::UNROLL)
+      for (int y = y0; y < y1; ++y) {
+        float4 ox = make_float4(0.f, 0.f, 0.f, 0.f), oy = ox, ol = ox;
+        float4 cu = make_float4(1.f, 1.f, 1.f, 1.f), cl = cu;
+        if (FULL || fm.up) { ox = ldg_stream(p_ux); oy = ldg_stream(p_ux + N); p_ux += W; }
+        if (FULL || fm.lat) { ol = ldg_stream(p_lat); p_lat += W; }
+        if (FULL || fm.up_conf) { cu = ldg_stream(p_cu); p_cu += W; }
+        if (FULL || fm.lat_conf) { cl = ldg_stream(p_cl); p_cl += W; }
+        row(ox, oy, ol, cu, cl, y);
       }
     }
   }
@@ -708,7 +766,7 @@ TileCfg tile_config(int B, int H, int W, int num_sms, int rows_override, int max
     t.rsub = 1; t.nwarps = 1;
     for (int d = 1; d <= max_warps; d++) if (NS % d == 0) t.nwarps = d;
   }
-  int rj = 48;  // rows walked by one warp per tile
+  int rj = 120;  // rows walked by one warp per tile (long tiles amortise the CTA prologue/epilogue)
   if (rows_override > 0) rj = std::max(1, rows_override / t.rsub);
   else
     while (rj > 4 && (int64_t)B * ((H + rj * t.rsub - 1) / (rj * t.rsub)) < 12ll * num_sms) rj /= 2;
@@ -750,14 +808,25 @@ int max_tiles_for(int H, int W) {
   return (H + 3) / 4 + 1;  // smallest auto tile is 4 rows (rsub == 1)
 }
 
+template <int MODEL, bool GEN_D, bool FULL, bool PACK>
+void launch_one(const PassArgs& a, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
+  static size_t configured = 0;  // opt in to > 48 KB of dynamic shared memory once per instantiation
+  if (smem > configured) {
+    cudaFuncSetAttribute(lm_pass_kernel<MODEL, GEN_D, FULL, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = smem;
+  }
+  lm_pass_kernel<MODEL, GEN_D, FULL, PACK><<<grid, block, smem, s>>>(a);
+}
+
 template <int MODEL, bool PACK>
 void launch_pass_model(const PassArgs& a, bool gen_d, bool full, dim3 grid, dim3 block, cudaStream_t s) {
+  const size_t smem = full ? (size_t)RING_STAGES * 5 * block.x * 16 : 0;
   if (gen_d) {
-    if (full) lm_pass_kernel<MODEL, true, true, PACK><<<grid, block, 0, s>>>(a);
-    else lm_pass_kernel<MODEL, true, false, PACK><<<grid, block, 0, s>>>(a);
+    if (full) launch_one<MODEL, true, true, PACK>(a, grid, block, smem, s);
+    else launch_one<MODEL, true, false, PACK>(a, grid, block, 0, s);
   } else {
-    if (full) lm_pass_kernel<MODEL, false, true, PACK><<<grid, block, 0, s>>>(a);
-    else lm_pass_kernel<MODEL, false, false, PACK><<<grid, block, 0, s>>>(a);
+    if (full) launch_one<MODEL, false, true, PACK>(a, grid, block, smem, s);
+    else launch_one<MODEL, false, false, PACK>(a, grid, block, 0, s);
   }
 }
 

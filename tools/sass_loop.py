@@ -10,6 +10,7 @@ import subprocess
 import sys
 
 lib, pat = sys.argv[1], sys.argv[2]
+MARK = sys.argv[3] if len(sys.argv) > 3 else "LDG"  # LDG: direct-load loop, LDS: cp.async ring loop
 txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
 funcs = re.split(r"\n\s*Function : ", txt)
 for f in funcs[1:]:
@@ -32,7 +33,8 @@ for f in funcs[1:]:
                 loops.append((addr[t], i))
     best = None
     for lo, hi in loops:
-        n128 = sum(1 for _, s in ins[lo:hi + 1] if "LDG" in s and ".128" in s)
+        n128 = sum(1 for _, s in ins[lo:hi + 1] if ("LDG" in s and ".128" in s and "LDGSTS" not in s) == (MARK == "LDG")
+                   and (MARK != "LDS" or ("LDS" in s and ".128" in s)))
         if n128 and (best is None or hi - lo < best[1] - best[0]):
             best = (lo, hi, n128)  # innermost loop that streams pixels
     print(f"== {name}: {len(ins)} instrs total")
@@ -47,7 +49,7 @@ for f in funcs[1:]:
         op = s.split()[0].split(".")[0]
         cnt[op] += 1
     px = n128 * 4 / 5.0  # 5 planes per 4 pixels
-    print(f"   loop [{ins[lo][0]:#x},{ins[hi][0]:#x}] {len(body)} instrs, {n128} LDG.128 -> {px:.0f} pixels/iter, {len(body)/px:.1f} instr/pixel")
+    print(f"   loop [{ins[lo][0]:#x},{ins[hi][0]:#x}] {len(body)} instrs, {n128} {MARK}.128 -> {px:.0f} pixels/iter, {len(body)/px:.1f} instr/pixel")
     fma = sum(cnt[k] for k in ("FFMA", "FMUL", "FADD", "FFMA2", "FMUL2", "FADD2"))
     alu = sum(cnt[k] for k in ("FMNMX", "FSEL", "FSETP", "IADD3", "IADD", "LOP3", "SHF", "IMAD", "MOV", "ISETP", "SEL", "LEA", "FMNMX3", "PRMT", "I2FP", "VIADD", "UMOV", "HFMA2"))
     print(f"   fp32-pipe {fma} ({fma/px:.1f}/px)  mufu {cnt['MUFU']} ({cnt['MUFU']/px:.1f}/px)  other-alu {alu} ({alu/px:.1f}/px)")
