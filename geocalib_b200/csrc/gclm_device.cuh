@@ -338,9 +338,9 @@ __device__ __forceinline__ void pixel_accumulate(const PassConst& pc, const Fiel
     // Huber (lm_optimizer.py:79-87): chi + 1e-8 == chi in fp32 for chi > 1
     const V mm = fmaxf(chi, 1.f);
     const V isx = fast_rsqrt(mm);
-    const V cost = fminf(chi, 1.f) * fmaf(2.f * mm, isx, splat<V>(-1.f));
+    // cost*conf = min(chi,1) (2 sqrt(max(chi,1)) - 1) conf = 2 chi w - min(chi,1) conf, w = conf/sqrt(max(chi,1))
     w_up = isx * cu;
-    acc[NH + NF] = fmaf(cost, cu, acc[NH + NF]);
+    acc[NH + NF] = fmaf(chi + chi, w_up, fmaf(-fminf(chi, 1.f), cu, acc[NH + NF]));
     // gravity columns: M z_j, z_j = (T0j - u T2j, T1j - v T2j)
     if constexpr (K == 0) {
       su_[0] = fmaf(Ap, pc.T00, fmaf(Bp, pc.T10, -pc.T20 * Nu));
@@ -394,9 +394,8 @@ __device__ __forceinline__ void pixel_accumulate(const PassConst& pc, const Fiel
     const V chi = r_lat * r_lat * inv_lat2;
     const V mm = fmaxf(chi, 1.f);
     const V isx = fast_rsqrt(mm);
-    const V cost = fminf(chi, 1.f) * fmaf(2.f * mm, isx, splat<V>(-1.f));
     w_lat = isx * cl;
-    acc[NH + NF + 1] = fmaf(cost, cl, acc[NH + NF + 1]);
+    acc[NH + NF + 1] = fmaf(chi + chi, w_lat, fmaf(-fminf(chi, 1.f), cl, acc[NH + NF + 1]));
     if constexpr (K == 0) {
       sl_[0] = im * fmaf(pc.T00, u, splat<V>(fmaf(pc.T10, v, pc.T20)));
       sl_[1] = im * fmaf(pc.T01, u, splat<V>(fmaf(pc.T11, v, pc.T21)));

@@ -15,6 +15,9 @@ __global__ void __launch_bounds__(256) k(float* out, long long* cyc, float x, fl
 #pragma unroll
   for (int i = 0; i < 8; i++) p[i] = make_float2(a[2 * i], a[2 * i + 1]);
   const float2 x2 = make_float2(x, x), y2 = make_float2(y, y);
+  float2 q[8], r[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) { q[i] = make_float2(x + i * 1e-6f, x - i * 1e-6f); r[i] = make_float2(y + i * 1e-6f, y - i * 1e-7f); }
   __syncthreads();
   const long long t0 = clock64();
 #pragma unroll 1
@@ -53,6 +56,21 @@ __global__ void __launch_bounds__(256) k(float* out, long long* cyc, float x, fl
       for (int i = 0; i < 8; i++) p[i] = __ffma2_rn(p[i], x2, y2);
 #pragma unroll
       for (int i = 0; i < 4; i++) asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+    } else if (MODE == 9) {  // 8 FFMA2, all operands packed register pairs (no broadcast)
+#pragma unroll
+      for (int i = 0; i < 8; i++) p[i] = __ffma2_rn(p[i], q[i], r[i]);
+    } else if (MODE == 10) {  // 8 FFMA2, one broadcast scalar operand
+#pragma unroll
+      for (int i = 0; i < 8; i++) p[i] = __ffma2_rn(p[i], x2, r[i]);
+    } else if (MODE == 11) {  // 16 scalar FFMA, three distinct registers
+#pragma unroll
+      for (int i = 0; i < 8; i++) { p[i].x = fmaf(p[i].x, q[i].x, r[i].x); p[i].y = fmaf(p[i].y, q[i].y, r[i].y); }
+    } else if (MODE == 12) {  // 8 FFMA2 with the accumulator as addend: p += q*r
+#pragma unroll
+      for (int i = 0; i < 8; i++) p[i] = __ffma2_rn(q[i], r[i], p[i]);
+    } else if (MODE == 13) {  // 16 scalar FFMA accumulate: a += b*c
+#pragma unroll
+      for (int i = 0; i < 8; i++) { p[i].x = fmaf(q[i].x, r[i].x, p[i].x); p[i].y = fmaf(q[i].y, r[i].y, p[i].y); }
     } else if (MODE == 8) {  // 8 FMUL2 + 8 FADD2
 #pragma unroll
       for (int i = 0; i < 8; i++) p[i] = __fmul2_rn(p[i], x2);
@@ -65,7 +83,7 @@ __global__ void __launch_bounds__(256) k(float* out, long long* cyc, float x, fl
 #pragma unroll
   for (int i = 0; i < 16; i++) s += a[i];
 #pragma unroll
-  for (int i = 0; i < 8; i++) s += p[i].x + p[i].y;
+  for (int i = 0; i < 8; i++) s += p[i].x + p[i].y + q[i].x + r[i].y;
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
   if (threadIdx.x == 0) cyc[blockIdx.x] = t1 - t0;
 }
@@ -94,7 +112,12 @@ void run(const char* name, int instr_per_iter, int ctas_per_sm) {
 }
 
 int main() {
-  for (int c : {2, 4, 8}) {
+  for (int c : {4}) {
+    run<9>("8 FFMA2 all-packed", 8, c);
+    run<10>("8 FFMA2 1 broadcast", 8, c);
+    run<11>("16 FFMA 3 distinct regs", 16, c);
+    run<12>("8 FFMA2 p+=q*r", 8, c);
+    run<13>("16 FFMA a+=b*c", 16, c);
     run<0>("16 FFMA", 16, c);
     run<1>("8 FFMA2 (same flops)", 8, c);
     run<2>("16 FFMA2 (2x flops)", 16, c);
