@@ -341,42 +341,35 @@ __device__ __forceinline__ void pixel_accumulate(const PassConst& pc, const Fiel
     // cost*conf = min(chi,1) (2 sqrt(max(chi,1)) - 1) conf = 2 chi w - min(chi,1) conf, w = conf/sqrt(max(chi,1))
     w_up = isx * cu;
     acc[NH + NF] = fmaf(chi + chi, w_up, fmaf(-fminf(chi, 1.f), cu, acc[NH + NF]));
-    // gravity columns: M z_j, z_j = (T0j - u T2j, T1j - v T2j)
+    // Jacobian columns.  With M z = s z + phi uv (uv.z) and z_j = (T0j - u T2j, T1j - v T2j):
+    //   s_j = T0j alpha + T1j beta - T2j gamma,  alpha = s Ap + phi Nu u, beta = s Bp + phi Nu v,
+    //   gamma = alpha u + beta v = Nu (s + phi r^2)        (Nu = Ap u + Bp v)
     if constexpr (K == 0) {
       su_[0] = fmaf(Ap, pc.T00, fmaf(Bp, pc.T10, -pc.T20 * Nu));
       su_[1] = fmaf(Ap, pc.T01, fmaf(Bp, pc.T11, -pc.T21 * Nu));
+      if constexpr (!GEN_D) su_[2] = pc.c * Nu;
+      else su_[2] = -pc.c * fmaf(Ap, dx, Bp * dy);
     } else {
-      const V z0x = fmaf(u, -pc.T20, splat<V>(pc.T00));
-      const float z0y = fmaf(-v, pc.T20, pc.T10);
-      const V z1x = fmaf(u, -pc.T21, splat<V>(pc.T01));
-      const float z1y = fmaf(-v, pc.T21, pc.T11);
       const V pn = m.phi * Nu;
-      su_[0] = fmaf(m.s, fmaf(Ap, z0x, Bp * z0y), pn * fmaf(u, z0x, v * z0y));
-      su_[1] = fmaf(m.s, fmaf(Ap, z1x, Bp * z1y), pn * fmaf(u, z1x, v * z1y));
-    }
-    // focal column
-    if constexpr (!GEN_D) {
-      if constexpr (K == 0) {
-        su_[2] = pc.c * Nu;
+      const V alpha = fmaf(pn, u, m.s * Ap), beta = fmaf(pn, v, m.s * Bp);
+      const V pr2 = m.phi * r2;
+      const V gamma = Nu * (m.s + pr2);
+      su_[0] = fmaf(alpha, pc.T00, fmaf(beta, pc.T10, -pc.T20 * gamma));
+      su_[1] = fmaf(alpha, pc.T01, fmaf(beta, pc.T11, -pc.T21 * gamma));
+      const V Np0 = fmaf(Ap, p0x, Bp * p0y);  // (n_perp . p0)/rho
+      const V iN = iota * Nu;
+      if constexpr (!GEN_D) {
+        // log-focal column (d = -uv): c gamma - iota Nu (Bc r^2 + A + phi) - phi r^2 Np0
+        V t;
+        if constexpr (MODEL == SIMPLE_RADIAL) t = (4.f * pc.k1) * iN;  // Bc = 0, A = phi = 2 k1
+        else t = iN * (fmaf(m.Bc, r2, m.A) + m.phi);
+        su_[2] = fmaf(-pr2, Np0, fmaf(pc.c, gamma, -t));
       } else {
-        const V Np0 = fmaf(Ap, p0x, Bp * p0y);
-        const V t = fmaf(pc.c, fmaf(m.phi, r2, m.s), -(iota * (fmaf(m.Bc, r2, m.A) + m.phi)));
-        su_[2] = fmaf(Nu, t, -(m.phi * r2 * Np0));
-      }
-    } else {
-      const V Nd = fmaf(Ap, dx, Bp * dy);
-      if constexpr (K == 0) {
-        su_[2] = -pc.c * Nd;
-      } else {
-        const V Np0 = fmaf(Ap, p0x, Bp * p0y);
+        const V Nd = fmaf(Ap, dx, Bp * dy);
         const V p0d = fmaf(p0x, dx, splat<V>(p0y * dy));
         const V t = fmaf(iota * m.Bc, uvd, m.phi * (p0d - pc.c * uvd));
         su_[2] = fmaf(fmaf(iota, m.A, -pc.c * m.s), Nd, fmaf(m.phi * uvd, Np0, Nu * t));
       }
-    }
-    if constexpr (K > 0) {
-      const V Np0 = fmaf(Ap, p0x, Bp * p0y);
-      const V iN = iota * Nu;
 #pragma unroll
       for (int k = 0; k < K; k++) su_[3 + k] = fmaf(m.sk[k], Np0, m.psi[k] * iN);
     }
