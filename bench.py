@@ -173,7 +173,7 @@ def host_threads():
 
 def cpu_baseline(model, h, w, iters, target_seconds=15.0):
     cores = host_threads()
-    probe_n = 8
+    probe_n = max(8, min(64, cores // 2))
     fields = cpu_sample_fields(model, probe_n, h, w, 99)
     dt = cpu_run(model, fields, iters)
     rate = probe_n / dt
@@ -195,7 +195,7 @@ def run_reference_arm(args, wl):
         return
     model, B, h, w, iters = wl
     cores = host_threads()
-    n = 8
+    n = max(8, min(64, cores // 2))  # enough (image, row-chunk) tasks to occupy every host thread
     fields = cpu_sample_fields(model, n, h, w, 99)
     probe = cpu_run(model, fields, iters)
     per_step = int(min(512, max(n, (n / probe) * 6.0)))  # ~6 s of CPU work per step

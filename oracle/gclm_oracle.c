@@ -497,7 +497,7 @@ static void eval_batch(const image_in *ims, int B, const char *skip, const REAL 
     if (log_focal && !rpf_basis) { fs[b][0] = fs[b][1] = R(1); }
     else { fs[b][0] = R(1) / cm[2]; fs[b][1] = R(1) / cm[3]; }
   }
-#pragma omp parallel for schedule(dynamic, 4)
+#pragma omp parallel for schedule(dynamic, 1)
   for (long t = 0; t < (long)B * nchunks; t++) {
     const int b = (int)(t / nchunks), c = (int)(t % nchunks);
     if (skip && skip[b]) continue;
