@@ -100,35 +100,6 @@ template <class V> __device__ __forceinline__ V splat(float s);
 template <> __device__ __forceinline__ float splat<float>(float s) { return s; }
 template <> __device__ __forceinline__ f2 splat<f2>(float s) { return f2(s); }
 
-// sin(x) for |x| <= 1.6 (latitudes live in [-pi/2, pi/2]): degree-9 odd polynomial, max abs
-// error 1.5e-7 against fp64 sin (coefficients: Chebyshev fit of (sin(x)/x - 1)/x^2 in x^2).
-__device__ __forceinline__ float sin_poly(float x) {
-  const float z = x * x;
-  float p = 2.6303815071e-06f;
-  p = fmaf(p, z, -1.9821368161e-04f);
-  p = fmaf(p, z, 8.3332318302e-03f);
-  p = fmaf(p, z, -1.6666665857e-01f);
-  return fmaf(x * z, p, x);
-}
-// Cold path (latitude outside the polynomial's range): exact sinf.  Scalar in / scalar out so that
-// nothing in the hot loop has its address taken (an array argument here costs STL/LDL per row).
-__device__ __noinline__ float sin_slow(float x) { return sinf(x); }
-// target_lat = sin(latitude_field) for 4 pixels (lm_optimizer.py:270)
-template <class V>
-__device__ __forceinline__ V sin_poly_v(V x) {
-  const V z = x * x;
-  V p = fmaf(z, 2.6303815071e-06f, splat<V>(-1.9821368161e-04f));
-  p = fmaf(p, z, splat<V>(8.3332318302e-03f));
-  p = fmaf(p, z, splat<V>(-1.6666665857e-01f));
-  return fmaf(x * z, p, x);
-}
-__device__ __forceinline__ void sin4(const float4 x, float& s0, float& s1, float& s2, float& s3) {
-  const f2 a = sin_poly_v(f2(x.x, x.y)), b = sin_poly_v(f2(x.z, x.w));
-  s0 = a.v.x; s1 = a.v.y; s2 = b.v.x; s3 = b.v.y;
-  const float mx = fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w)));
-  if (mx > 1.6f) { s0 = sin_slow(x.x); s1 = sin_slow(x.y); s2 = sin_slow(x.z); s3 = sin_slow(x.w); }
-}
-
 // ------------------------------------------------------------------------------------------
 // per-image constants of one pass (hoisted out of the pixel loop)
 // ------------------------------------------------------------------------------------------

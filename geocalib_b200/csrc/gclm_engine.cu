@@ -165,6 +165,7 @@ __device__ __noinline__ void finalize_image(const PassArgs& a, int b, const floa
   if (a.res.gravity) for (int i = 0; i < 3; i++) a.res.gravity[(size_t)b * 3 + i] = Pb[8 + i];
   if (a.res.stop_at)
     a.res.stop_at[b] = (a.stop_mode == GCLM_STOP_PER_IMAGE && !a.shared) ? a.stop_at[b] : a.ctrl->stop_at;
+  if (!isfinite(cu + cl)) fl |= GCLM_STATUS_NONFINITE;  // NaN/Inf in the fields or a diverged estimate
   if (a.res.status) a.res.status[b] = fl;
   (void)K;
 }

@@ -500,3 +500,38 @@ def test_shared_intrinsics_two_gpus(dev):
     for rank, cam_full, g_full, cam_part, g_part, lo, hi in got:
         np.testing.assert_allclose(cam_part[:, 3], cam_full[lo:hi, 3], rtol=2e-6)
         np.testing.assert_allclose(g_part, g_full[lo:hi], atol=2e-6)
+
+
+def test_nonfinite_input_is_flagged_not_raised(dev):
+    """Numerical failure never raises (lm_optimizer.py:129-133, 497-499): a NaN in one image's fields
+    flags THAT image (status bit 4 / Cholesky bit) and leaves the others untouched."""
+    import geocalib_b200 as G
+    from geocalib_b200 import _lib
+
+    cam, grav = synth_params("pinhole", 3, 64, 128, 4)
+    f = render_on_device("pinhole", cam, grav, 64, 128, dev, sigma=0.02, seed=1)
+    clean = G.LMOptimizer({"camera_model": "pinhole", "num_steps": 8, "early_stop": False}).eval()(f)
+    f["latitude_field"][1, 0, 10, 17] = float("nan")
+    out = G.LMOptimizer({"camera_model": "pinhole", "num_steps": 8, "early_stop": False}).eval()(f)
+    torch.cuda.synchronize()
+    st = out["status"].cpu().numpy()
+    assert st[1] & _lib.STATUS_NONFINITE and st[1] & _lib.STATUS_CHOLESKY_FAILED
+    assert st[0] == 0 and st[2] == 0
+    assert torch.equal(out["camera"]._data[[0, 2]], clean["camera"]._data[[0, 2]])
+
+
+def test_latitude_outside_half_pi(dev):
+    """target_lat = sin(latitude_field) is exact for ANY input range (the engine computes it once per
+    solve with sinf): shifting the latitude field by 2*pi must not change the result."""
+    import geocalib_b200 as G
+
+    cam, grav = synth_params("pinhole", 2, 64, 128, 6)
+    f = render_on_device("pinhole", cam, grav, 64, 128, dev, sigma=0.02, seed=2)
+    opt = G.LMOptimizer({"camera_model": "pinhole", "num_steps": 10, "early_stop": False}).eval()
+    a = opt(f)
+    g = dict(f)
+    g["latitude_field"] = f["latitude_field"] + 2 * np.pi
+    b = opt(g)
+    torch.cuda.synchronize()
+    assert torch.allclose(a["camera"]._data, b["camera"]._data, rtol=2e-5)
+    assert torch.allclose(a["gravity"]._data, b["gravity"]._data, atol=2e-5)

@@ -53,4 +53,7 @@ for f in funcs[1:]:
     fma = sum(cnt[k] for k in ("FFMA", "FMUL", "FADD", "FFMA2", "FMUL2", "FADD2"))
     alu = sum(cnt[k] for k in ("FMNMX", "FSEL", "FSETP", "IADD3", "IADD", "LOP3", "SHF", "IMAD", "MOV", "ISETP", "SEL", "LEA", "FMNMX3", "PRMT", "I2FP", "VIADD", "UMOV", "HFMA2"))
     print(f"   fp32-pipe {fma} ({fma/px:.1f}/px)  mufu {cnt['MUFU']} ({cnt['MUFU']/px:.1f}/px)  other-alu {alu} ({alu/px:.1f}/px)")
+    # FP32-pipe cost model from tools/ubench_fp32x2.cu (1 / measured warp-instr per clk per SM)
+    cost = 0.65 * cnt["FFMA2"] + 0.306 * (cnt["FMUL2"] + cnt["FADD2"]) + 0.37 * (cnt["FFMA"] + cnt["FMUL"] + cnt["FADD"])
+    print(f"   fp32-pipe cost model: {cost/px:.1f} clk/32px  (HBM roofline = 28.3 clk/32px at 1965 MHz)")
     print("   " + ", ".join(f"{k}:{v}" for k, v in cnt.most_common()))

@@ -56,6 +56,37 @@ __global__ void __launch_bounds__(256) k(float* out, long long* cyc, float x, fl
       for (int i = 0; i < 8; i++) p[i] = __ffma2_rn(p[i], x2, y2);
 #pragma unroll
       for (int i = 0; i < 4; i++) asm volatile("rsqrt.approx.ftz.f32 %0, %0;" : "+f"(a[i]));
+    } else if (MODE == 14) {  // 8 FFMA2 + 8 scalar FFMA
+#pragma unroll
+      for (int i = 0; i < 8; i++) p[i] = __ffma2_rn(p[i], x2, y2);
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = fmaf(a[i], x, y);
+    } else if (MODE == 15) {  // 8 FFMA2 + 8 scalar FMUL
+#pragma unroll
+      for (int i = 0; i < 8; i++) p[i] = __ffma2_rn(p[i], x2, y2);
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = a[i] * x;
+    } else if (MODE == 16) {  // 8 FFMA2 + 8 scalar FADD
+#pragma unroll
+      for (int i = 0; i < 8; i++) p[i] = __ffma2_rn(p[i], x2, y2);
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = a[i] + y;
+    } else if (MODE == 17) {  // 16 scalar FMUL
+#pragma unroll
+      for (int i = 0; i < 16; i++) a[i] = a[i] * x;
+    } else if (MODE == 18) {  // 16 scalar FADD
+#pragma unroll
+      for (int i = 0; i < 16; i++) a[i] = a[i] + y;
+    } else if (MODE == 19) {  // 8 FFMA2 + 16 scalar FFMA
+#pragma unroll
+      for (int i = 0; i < 8; i++) p[i] = __ffma2_rn(p[i], x2, y2);
+#pragma unroll
+      for (int i = 0; i < 16; i++) a[i] = fmaf(a[i], x, y);
+    } else if (MODE == 20) {  // 8 FMUL2 + 8 scalar FFMA
+#pragma unroll
+      for (int i = 0; i < 8; i++) p[i] = __fmul2_rn(p[i], x2);
+#pragma unroll
+      for (int i = 0; i < 8; i++) a[i] = fmaf(a[i], x, y);
     } else if (MODE == 9) {  // 8 FFMA2, all operands packed register pairs (no broadcast)
 #pragma unroll
       for (int i = 0; i < 8; i++) p[i] = __ffma2_rn(p[i], q[i], r[i]);
@@ -113,6 +144,13 @@ void run(const char* name, int instr_per_iter, int ctas_per_sm) {
 
 int main() {
   for (int c : {4}) {
+    run<14>("8 FFMA2 + 8 FFMA", 16, c);
+    run<15>("8 FFMA2 + 8 FMUL", 16, c);
+    run<16>("8 FFMA2 + 8 FADD", 16, c);
+    run<17>("16 FMUL", 16, c);
+    run<18>("16 FADD", 16, c);
+    run<19>("8 FFMA2 + 16 FFMA", 24, c);
+    run<20>("8 FMUL2 + 8 FFMA", 16, c);
     run<9>("8 FFMA2 all-packed", 8, c);
     run<10>("8 FFMA2 1 broadcast", 8, c);
     run<11>("16 FFMA 3 distinct regs", 16, c);
