@@ -201,22 +201,9 @@ __device__ __noinline__ void divisional_literal(float k1, float r2, ModelScalars
   m.om[0] = -r2 / mf(dn * dn);
 }
 
-// per-lane cold-path fix-up of the divisional scalars
-__device__ __forceinline__ void divisional_fixup(float k1, float r2, float x, ModelScalars<1, float>& m) {
-  if (k1 == 0.f || x < 1e-6f) divisional_literal(k1, r2, m);
-}
-__device__ __forceinline__ void divisional_fixup(float k1, f2 r2, f2 x, ModelScalars<1, f2>& m) {
-  if (k1 == 0.f || x.v.x < 1e-6f || x.v.y < 1e-6f) {
-    ModelScalars<1, float> a, b;
-    divisional_literal(k1, r2.v.x, a);
-    divisional_literal(k1, r2.v.y, b);
-    m.s = f2(a.s, b.s); m.phi = f2(a.phi, b.phi); m.A = f2(a.A, b.A); m.Bc = f2(a.Bc, b.Bc);
-    m.su = f2(a.su, b.su); m.Q = f2(a.Q, b.Q);
-    m.sk[0] = f2(a.sk[0], b.sk[0]); m.psi[0] = f2(a.psi[0], b.psi[0]); m.om[0] = f2(a.om[0], b.om[0]);
-  }
-}
-
-template <int MODEL, class V>
+// LIT (simple_divisional, scalar only): evaluate the reference's literal masked formulas instead of
+// the closed form -- taken for pixels where the closed form does not apply (see divisional_is_cold).
+template <int MODEL, class V, bool LIT = false>
 __device__ __forceinline__ void model_scalars(const PassConst& pc, V r2, ModelScalars<num_dist(MODEL), V>& m) {
   if constexpr (MODEL == PINHOLE) {  // camera.py:532-562 (never read: the K == 0 paths use constants)
     m.s = splat<V>(1.f); m.phi = m.A = m.Bc = m.Q = splat<V>(0.f); m.su = splat<V>(1.f);
@@ -244,6 +231,11 @@ __device__ __forceinline__ void model_scalars(const PassConst& pc, V r2, ModelSc
     //   s = 2/w, phi = A = 8 k1/(t w^2), Bc = 32 k1^2 (1+3t)/(t^3 w^3),
     //   ds/dk = 4 r^2/(t w^2), psi = 4 (1 + 2t - t^2)/(t^3 w^2).
     // The literal masked formulas (cold path) take over when k1 == 0 or the root is clamped.
+    if constexpr (LIT) {
+      static_assert(!LIT || !is_f2<V>::value, "literal path is scalar");
+      if constexpr (!is_f2<V>::value) divisional_literal(pc.k1, r2, m);
+      return;
+    }
     const V x = fmaf(-4.f * pc.k1, r2, splat<V>(1.f));
     const V xs = fmaxf(x, 1e-6f);
     const V it = fast_rsqrt(xs), t = xs * it, w = 1.f + t, iw = fast_rcp(w);
@@ -257,7 +249,6 @@ __device__ __forceinline__ void model_scalars(const PassConst& pc, V r2, ModelSc
     m.su = su;
     m.Q = (-2.f * pc.k1) * su * su;
     m.om[0] = -(r2 * su * su);
-    divisional_fixup(pc.k1, r2, x, m);
   }
 }
 
@@ -269,7 +260,7 @@ __device__ __forceinline__ void model_scalars(const PassConst& pc, V r2, ModelSc
 // ------------------------------------------------------------------------------------------
 struct FieldMask { bool up, lat, up_conf, lat_conf; };
 
-template <int MODEL, bool GEN_D, bool FULL, class V>
+template <int MODEL, bool GEN_D, bool FULL, class V, bool LIT = false>
 __device__ __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMask fm, V u,
                                                  float v, V ox, V oy, V sin_olat, V cu,
                                                  V cl, float inv_up2, float inv_lat2,
@@ -278,7 +269,7 @@ __device__ __forceinline__ void pixel_accumulate(const PassConst& pc, const Fiel
   const bool has_up = FULL || fm.up, has_lat = FULL || fm.lat;
   const V r2 = fmaf(u, u, splat<V>(v * v));
   ModelScalars<K, V> m;
-  model_scalars<MODEL, V>(pc, r2, m);
+  model_scalars<MODEL, V, LIT>(pc, r2, m);
 
   V su_[NF], sl_[NF];  // Jacobian row scalars (up: along n_perp; latitude)
   V e = splat<V>(0.f), w_up = e, r_lat = e, w_lat = e;
@@ -415,6 +406,26 @@ __device__ __forceinline__ void pixel_accumulate(const PassConst& pc, const Fiel
     if (has_lat) g = fmaf(wl[i], r_lat, g);
     acc[NH + i] = g;
   }
+}
+
+// simple_divisional: does pixel (u, v) need the literal masked formulas?  k1 == 0 (trivial init:
+// every masked branch fires) or 1 - 4 k1 r^2 < 1e-6 (clamped square root).
+__device__ __forceinline__ bool divisional_is_cold(const PassConst& pc, float u, float v) {
+  return pc.k1 == 0.f || fmaf(-4.f * pc.k1, fmaf(u, u, v * v), 1.f) < 1e-6f;
+}
+// Cold path: one pixel through the scalar code with the literal formulas; returns its contribution
+// in d[NACC] (local memory is fine here) so that the hot loop's packed accumulators never have
+// their address taken.
+template <int MODEL, bool GEN_D, bool FULL, bool LIT>
+__device__ __noinline__ void pixel_scalar(const PassConst& pc, const FieldMask fm, float u, float v, float ox,
+                                           float oy, float sin_olat, float cu, float cl, float inv_up2,
+                                           float inv_lat2, float* d) {
+  float a1[Dims<MODEL>::NACC];
+#pragma unroll
+  for (int i = 0; i < Dims<MODEL>::NACC; i++) a1[i] = 0.f;
+  pixel_accumulate<MODEL, GEN_D, FULL, float, LIT>(pc, fm, u, v, ox, oy, sin_olat, cu, cl, inv_up2, inv_lat2, a1);
+#pragma unroll
+  for (int i = 0; i < Dims<MODEL>::NACC; i++) d[i] = a1[i];
 }
 
 // ------------------------------------------------------------------------------------------

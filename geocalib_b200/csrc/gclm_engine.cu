@@ -492,6 +492,27 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
       const float v = ((float)y - pc.cy) * pc.inv_fy;
       // `ol` already holds target_lat = sin(latitude_field): sin_plane_kernel ran once before pass 0
       const float sl0 = ol.x, sl1 = ol.y, sl2 = ol.z, sl3 = ol.w;
+      if constexpr (MODEL == SIMPLE_DIVISIONAL) {
+        // rare pixels (all of them only while k1 == 0, i.e. the first pass from the trivial init) go
+        // through the literal masked formulas, one at a time
+        const bool c0 = divisional_is_cold(pc, u[0], v), c1 = divisional_is_cold(pc, u[1], v);
+        const bool c2 = divisional_is_cold(pc, u[2], v), c3 = divisional_is_cold(pc, u[3], v);
+        if (c0 | c1 | c2 | c3) {
+          float d[NACC];
+          const float us[4] = {u[0], u[1], u[2], u[3]};
+          const float oxs[4] = {ox.x, ox.y, ox.z, ox.w}, oys[4] = {oy.x, oy.y, oy.z, oy.w};
+          const float sls[4] = {sl0, sl1, sl2, sl3}, cus[4] = {cu.x, cu.y, cu.z, cu.w}, cls[4] = {cl.x, cl.y, cl.z, cl.w};
+          const bool cold[4] = {c0, c1, c2, c3};
+#pragma unroll 1
+          for (int i = 0; i < 4; i++) {
+            if (cold[i]) pixel_scalar<MODEL, GEN_D, FULL, true>(pc, fm, us[i], v, oxs[i], oys[i], sls[i], cus[i], cls[i], inv_up2, inv_lat2, d);
+            else pixel_scalar<MODEL, GEN_D, FULL, false>(pc, fm, us[i], v, oxs[i], oys[i], sls[i], cus[i], cls[i], inv_up2, inv_lat2, d);
+#pragma unroll
+            for (int k = 0; k < NACC; k++) acc[k] = acc[k] + splat<V>(0.5f * d[k]);  // both halves sum to d
+          }
+          return;
+        }
+      }
       if constexpr (PACK) {
         pixel_accumulate<MODEL, GEN_D, FULL, f2>(pc, fm, f2(u[0], u[1]), v, f2(ox.x, ox.y), f2(oy.x, oy.y),
                                                  f2(sl0, sl1), f2(cu.x, cu.y), f2(cl.x, cl.y), inv_up2, inv_lat2, acc);
@@ -663,7 +684,8 @@ __global__ void render_kernel(int B, int H, int W, const float* cam, const float
   const float u = ((float)x - pc.cx) / c[2], v = ((float)y - pc.cy) / c[3];
   const float r2 = u * u + v * v;
   ModelScalars<num_dist(MODEL), float> m;
-  model_scalars<MODEL, float>(pc, r2, m);
+  if (MODEL == SIMPLE_DIVISIONAL && divisional_is_cold(pc, u, v)) model_scalars<MODEL, float, MODEL == SIMPLE_DIVISIONAL>(pc, r2, m);
+  else model_scalars<MODEL, float>(pc, r2, m);
   const float p0x = g[0] - g[2] * u, p0y = g[1] - g[2] * v;
   const float iota = u * p0x + v * p0y;
   float px = m.s * p0x + m.phi * iota * u, py = m.s * p0y + m.phi * iota * v;
