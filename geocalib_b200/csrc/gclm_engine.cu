@@ -90,6 +90,28 @@ __device__ __forceinline__ void cp_async16(unsigned dst_smem, const float* src) 
   asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers (GCLM_TMA build) ----
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+// Bounded wait: a mis-programmed transaction count must never hang the GPU (returns false instead).
+__device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity) {
+  for (unsigned spin = 0; spin < (1u << 26); ++spin) {
+    unsigned ok;
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    if (ok) return true;
+  }
+  return false;
+}
+
 __device__ __forceinline__ float4 lds128(unsigned addr) {
   float4 r;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
@@ -470,11 +492,27 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
 #pragma unroll
   for (int i = 0; i < NACC; i++) acc[i] = splat<V>(0.f);
 
+#ifdef GCLM_TMA
+  unsigned tma_it = 0;  // rows issued == rows consumed so far by this warp (ring position / phase)
+  if (FULL && RING_STAGES > 0) {
+    if (lane == 0) {
+      const unsigned bars0 = smem_u32 + (unsigned)nwarps * (RING_STAGES * 5u * 512u) + (unsigned)warp * (RING_STAGES * 8u);
+      for (int k = 0; k < RING_STAGES; k++) mbar_init(bars0 + k * 8u, 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+  }
+#endif
   for (int job = warp; job < NS * a.rsub; job += nwarps) {
     const int strip = job % NS, sub = job / NS;
     const int x0 = (strip << 7) + (lane << 2);
     const int y0 = yt0 + sub * RJ, y1 = min(yt1, y0 + RJ);
+#ifdef GCLM_TMA
+    if (!FULL && x0 >= W) continue;
+#else
     if (x0 >= W) continue;  // W % 4 == 0 is enforced on the host
+#endif
     float u[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) u[i] = ((float)(x0 + i) - pc.cx) * pc.inv_fx;
@@ -525,6 +563,49 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
         pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[3], v, ox.w, oy.w, sl3, cu.w, cl.w, inv_up2, inv_lat2, acc);
       }
     };
+#ifdef GCLM_TMA
+    if constexpr (FULL && RING_STAGES > 0) {
+      // ---- TMA ring: lane 0 of the warp issues ONE bulk copy per plane per row (the strip's 512 B,
+      // cp.async.bulk global->shared, completion on a per-stage mbarrier), RING_STAGES rows ahead;
+      // all lanes wait on the stage's mbarrier phase and read their float4 with LDS.128.
+      const unsigned nb = (unsigned)min(128, W - (strip << 7)) * 4u;  // bytes of this strip per plane-row
+      const unsigned wbase = smem_u32 + (unsigned)warp * (RING_STAGES * 5u * 512u);
+      const unsigned bars = smem_u32 + (unsigned)nwarps * (RING_STAGES * 5u * 512u) + (unsigned)warp * (RING_STAGES * 8u);
+      const float* g_ux = a.up + (size_t)b * 2 * N + (size_t)y0 * W + (strip << 7);
+      const float* g_lat = a.lat + (size_t)b * N + (size_t)y0 * W + (strip << 7);
+      const float* g_cu = a.uconf + (size_t)b * N + (size_t)y0 * W + (strip << 7);
+      const float* g_cl = a.lconf + (size_t)b * N + (size_t)y0 * W + (strip << 7);
+      auto issue = [&](unsigned st, int yy) {  // executed by lane 0 only
+        const size_t o = (size_t)(yy - y0) * W;
+        const unsigned d = wbase + st * (5u * 512u), bar = bars + st * 8u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, 5u * nb);
+        bulk_g2s(d, g_ux + o, nb, bar); bulk_g2s(d + 512u, g_ux + N + o, nb, bar);
+        bulk_g2s(d + 1024u, g_lat + o, nb, bar);
+        bulk_g2s(d + 1536u, g_cu + o, nb, bar); bulk_g2s(d + 2048u, g_cl + o, nb, bar);
+      };
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < RING_STAGES; k++)
+          if (y0 + k < y1) issue((tma_it + k) % RING_STAGES, y0 + k);
+      }
+      const bool active = x0 < W;
+#pragma unroll 1
+      for (int y = y0; y < y1; ++y) {
+        const unsigned st = tma_it % RING_STAGES, par = (tma_it / RING_STAGES) & 1u;
+        if (!mbar_wait(bars + st * 8u, par)) { a.flags[b] |= GCLM_STATUS_NONFINITE; }
+        const unsigned d = wbase + st * (5u * 512u) + (unsigned)lane * 16u;
+        if (active) {
+          const float4 ox = lds128(d), oy = lds128(d + 512u), ol = lds128(d + 1024u);
+          const float4 cu = lds128(d + 1536u), cl = lds128(d + 2048u);
+          row(ox, oy, ol, cu, cl, y);
+        }
+        __syncwarp();  // every lane is done with this stage before it is refilled
+        if (lane == 0 && y + RING_STAGES < y1) issue(st, y + RING_STAGES);
+        ++tma_it;
+      }
+    } else
+#endif
     if constexpr (FULL && RING_STAGES > 0) {
       // ---- cp.async (LDGSTS) ring: every lane prefetches ITS float4 of each of the 5 planes
       // STAGES rows ahead into a private shared-memory slot (no barriers: a lane only ever reads
@@ -855,7 +936,7 @@ void launch_one(const PassArgs& a, dim3 grid, dim3 block, size_t smem, cudaStrea
 
 template <int MODEL, bool PACK>
 void launch_pass_model(const PassArgs& a, bool gen_d, bool full, dim3 grid, dim3 block, cudaStream_t s) {
-  const size_t smem = full ? (size_t)RING_STAGES * 5 * block.x * 16 : 0;
+  const size_t smem = full ? (size_t)RING_STAGES * 5 * block.x * 16 + (size_t)(block.x / 32) * RING_STAGES * 8 : 0;
   if (gen_d) {
     if (full) launch_one<MODEL, true, true, PACK>(a, grid, block, smem, s);
     else launch_one<MODEL, true, false, PACK>(a, grid, block, 0, s);
