@@ -198,7 +198,9 @@ def run_reference_arm(args, wl):
     n = max(8, min(64, cores // 2))  # enough (image, row-chunk) tasks to occupy every host thread
     fields = cpu_sample_fields(model, n, h, w, 99)
     probe = cpu_run(model, fields, iters)
-    per_step = int(min(512, max(n, (n / probe) * 6.0)))  # ~6 s of CPU work per step
+    # one step = a bounded sample: ~12 s of CPU work, at least 2 images per host thread so that the
+    # (image, row-chunk) task pool keeps all threads busy (throughput still rises with sample size)
+    per_step = int(min(512, max(n, 2 * cores if cores <= 128 else cores, (n / probe) * 12.0)))
     if per_step != n:
         fields = cpu_sample_fields(model, per_step, h, w, 99)
     for _ in range(min(args.warmup, 1)):
