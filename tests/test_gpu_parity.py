@@ -535,3 +535,71 @@ def test_latitude_outside_half_pi(dev):
     torch.cuda.synchronize()
     assert torch.allclose(a["camera"]._data, b["camera"]._data, rtol=2e-5)
     assert torch.allclose(a["gravity"]._data, b["gravity"]._data, atol=2e-5)
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_outliers_and_clamps_vs_oracle(dev, model):
+    """Huber branch exercised hard (25 % outlier pixels, chi >> 1), tiny and huge fields of view that
+    run into the vfov clamp (camera.py:140-145), distortion pushed against its clamp: fixed 25
+    iterations, engine vs oracle."""
+    import geocalib_b200 as G
+
+    h, w, B = 96, 128, 6
+    cam, grav = synth_params(model, B, h, w, 77)
+    cam[0, 2:4] = h / 2 / np.tan(np.deg2rad(7.0) / 2)     # narrow: close to the 5 deg clamp
+    cam[1, 2:4] = h / 2 / np.tan(np.deg2rad(140.0) / 2)   # wide: close to the 150 deg clamp
+    if model in ("simple_radial", "radial"):
+        cam[2, 6] = 0.6                                    # near the +-0.7 distortion clamp
+    cam[1, 6:] = 0.0                                       # keep the 140 deg image well-posed
+    f = render_on_device(model, cam, grav, h, w, dev, sigma=0.03, seed=21)
+    rng = torch.Generator(device=dev).manual_seed(5)
+    mask = torch.rand((B, 1, h, w), device=dev, generator=rng) < 0.25
+    noise_up = torch.nn.functional.normalize(torch.randn((B, 2, h, w), device=dev, generator=rng), dim=1)
+    f["up_field"] = torch.where(mask, noise_up, f["up_field"]).contiguous()
+    f["latitude_field"] = torch.where(mask, (torch.rand((B, 1, h, w), device=dev, generator=rng) - 0.5) * 3.0,
+                                      f["latitude_field"]).contiguous()
+    conf = {"num_steps": 25, "early_stop": False}
+    with torch.no_grad():
+        out = G.LMOptimizer({"camera_model": model, **conf}).eval()(f)
+    torch.cuda.synchronize()
+    fn = {k: v.cpu().numpy() for k, v in f.items()}
+    ref = oracle.lm(model, fn["up_field"], fn["latitude_field"], fn["up_confidence"], fn["latitude_confidence"], conf=conf)
+    assert int(out["status"].sum()) == 0
+    np.testing.assert_allclose(out["final_cost"].cpu().numpy(), ref["final_cost"], rtol=1e-3)
+    assert_params_close(out["camera"]._data.cpu().numpy(), out["gravity"]._data.cpu().numpy(),
+                        ref["camera"], ref["gravity"], model, tol=2e-4)
+
+
+def test_cuda_graph_capture_and_replay(dev):
+    """After gclm_reserve the solve allocates nothing and never synchronises: the whole
+    num_steps+1-launch sequence can be captured into a CUDA graph and replayed on new data."""
+    import geocalib_b200 as G
+    from geocalib_b200.engine import get_engine
+
+    model, h, w, B = "pinhole", 96, 128, 4
+    cam, grav = synth_params(model, B, h, w, 9)
+    f1 = render_on_device(model, cam, grav, h, w, dev, sigma=0.02, seed=1)
+    f2 = render_on_device(model, cam, grav, h, w, dev, sigma=0.02, seed=2)
+    opt = G.LMOptimizer({"camera_model": model, "num_steps": 10, "early_stop": False}).eval()
+    get_engine(dev).reserve(B, h, w)
+    static = {k: v.clone() for k, v in f1.items()}
+    with torch.no_grad():
+        ref1, ref2 = opt(f1), opt(f2)
+        torch.cuda.synchronize()
+        s = torch.cuda.Stream(dev)
+        s.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(s):
+            opt(static)  # warm-up on the side stream
+        torch.cuda.current_stream(dev).wait_stream(s)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = opt(static)
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out["camera"]._data, ref1["camera"]._data)
+        for k in static:
+            static[k].copy_(f2[k])
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out["camera"]._data, ref2["camera"]._data)
+        assert torch.equal(out["gravity"]._data, ref2["gravity"]._data)
