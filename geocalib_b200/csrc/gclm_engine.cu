@@ -87,7 +87,13 @@ __device__ __forceinline__ float4 ldg_stream(const float* p) {
 }
 
 __device__ __forceinline__ void cp_async16(unsigned dst_smem, const float* src) {
+#if defined(GCLM_CPASYNC_L2_128)
+  asm volatile("cp.async.cg.shared.global.L2::128B [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+#elif defined(GCLM_CPASYNC_L2_NONE)
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+#else
   asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+#endif
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers (GCLM_TMA build) ----
