@@ -56,7 +56,8 @@ struct Ctrl {
 
 struct PassArgs {
   const float *up, *lat, *uconf, *lconf;
-  int B, H, W;
+  int B, H, W;          // W is the row pitch the kernels walk (padded to a multiple of 4 when repacked)
+  int Wt;               // true image width (cost normalisation)
   int rows_per_tile, tiles_per_image, rsub;
   int pass, is_final, shared;
   int model, num_steps, early_stop, fix_lambda, spherical, log_focal, stop_mode;
@@ -138,7 +139,7 @@ __device__ __forceinline__ int active_columns(int model, int est_gravity, int es
 template <int MODEL>
 __device__ __noinline__ void finalize_image(const PassArgs& a, int b, const float* sums, int sl) {
   constexpr int K = Dims<MODEL>::K, NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH;
-  const float invN = 1.f / ((float)a.H * (float)a.W);
+  const float invN = 1.f / ((float)a.H * (float)a.Wt);
   const float cu = sums[NH + NF] * (a.up_scale * a.up_scale) * invN;
   const float cl = sums[NH + NF + 1] * (a.lat_scale * a.lat_scale) * invN;
   const float* Pb = a.P + ((size_t)b * 2 + sl) * PSTRIDE;
@@ -233,7 +234,7 @@ __device__ __noinline__ void lm_step_image(const PassArgs& a, int b, const float
     finalize_image<MODEL>(a, b, sums, sl);
     return;
   }
-  const float invN = 1.f / ((float)a.H * (float)a.W);
+  const float invN = 1.f / ((float)a.H * (float)a.Wt);
   const float cu = sums[NH + NF] * (a.up_scale * a.up_scale) * invN;
   const float cl = sums[NH + NF + 1] * (a.lat_scale * a.lat_scale) * invN;
   const float cost = cu + cl;  // lm_optimizer.py:584,610
@@ -311,7 +312,7 @@ __device__ __noinline__ void lm_step_image(const PassArgs& a, int b, const float
 template <int MODEL>
 __device__ __noinline__ void schur_image(const PassArgs& a, int b, const float* sums) {
   constexpr int NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH;
-  const float invN = 1.f / ((float)a.H * (float)a.W);
+  const float invN = 1.f / ((float)a.H * (float)a.Wt);
   const float cu = sums[NH + NF] * (a.up_scale * a.up_scale) * invN;
   const float cl = sums[NH + NF + 1] * (a.lat_scale * a.lat_scale) * invN;
   const float cost = cu + cl;
@@ -737,6 +738,32 @@ __global__ void __launch_bounds__(256) sin_plane_kernel(const float4* __restrict
   }
 }
 
+// Widths that are not a multiple of 4 (or planes that are not 16-byte aligned) cannot be walked with
+// float4: the fields are copied ONCE per solve into engine scratch with the row pitch padded to a
+// multiple of 4.  Padding pixels get confidence 0 (weight and cost contributions vanish exactly);
+// missing confidence planes become 1, a missing field becomes 0 with confidence 0; sin() of the
+// latitude is folded in.  After this every pass runs the aligned 5-plane fast path.
+__global__ void __launch_bounds__(256) repack_kernel(int B, int H, int W, int Wp, const float* up, const float* lat,
+                                                     const float* uconf, const float* lconf, float* o_up,
+                                                     float* o_sinlat, float* o_uconf, float* o_lconf) {
+  const size_t total = (size_t)B * H * Wp;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int x = (int)(i % Wp);
+    const size_t by = i / Wp;
+    const int y = (int)(by % H);
+    const size_t b = by / H;
+    const bool in = x < W;
+    const size_t src = ((size_t)b * H + y) * W + x;       // (b, y, x) in a (B, H, W) plane
+    const size_t Np = (size_t)H * Wp, N = (size_t)H * W;
+    const size_t dst = (size_t)y * Wp + x;
+    o_up[b * 2 * Np + dst] = (in && up) ? up[b * 2 * N + (size_t)y * W + x] : 0.f;
+    o_up[b * 2 * Np + Np + dst] = (in && up) ? up[b * 2 * N + N + (size_t)y * W + x] : 0.f;
+    o_sinlat[b * Np + dst] = (in && lat) ? sinf(lat[src]) : 0.f;
+    o_uconf[b * Np + dst] = (in && up) ? (uconf ? uconf[src] : 1.f) : 0.f;
+    o_lconf[b * Np + dst] = (in && lat) ? (lconf ? lconf[src] : 1.f) : 0.f;
+  }
+}
+
 // counter-based RNG for the synthetic generator (splitmix64 finaliser)
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z += 0x9e3779b97f4a7c15ull;
@@ -874,7 +901,7 @@ struct gclm_comm {
 namespace {
 
 struct Layout {  // carve the scratch buffer
-  size_t P, lam, prev, cost0, slot, flags, stop_at, tickets, ctrl, partials, schur, sinlat, total;
+  size_t P, lam, prev, cost0, slot, flags, stop_at, tickets, ctrl, partials, schur, sinlat, repack, total;
 };
 
 struct TileCfg { int nwarps, rsub, rows_per_tile, tiles_per_image; };
@@ -896,7 +923,7 @@ TileCfg tile_config(int B, int H, int W, int num_sms, int rows_override, int max
   return t;
 }
 
-Layout make_layout(int B, int max_tiles, size_t pixels) {
+Layout make_layout(int B, int max_tiles, size_t pixels, bool repack) {
   Layout L;
   size_t o = 0;
   auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 255) & ~size_t(255); return r; };
@@ -912,6 +939,7 @@ Layout make_layout(int B, int max_tiles, size_t pixels) {
   L.partials = take(sizeof(float) * (size_t)B * max_tiles * MAX_NACC);
   L.schur = take(sizeof(float) * (size_t)B * SCHUR_STRIDE + 4096);
   L.sinlat = take(sizeof(float) * (size_t)B * pixels);
+  L.repack = take(repack ? sizeof(float) * (size_t)B * pixels * 4 : 0);  // up (2 planes) + 2 confidences
   L.total = o;
   return L;
 }
@@ -983,26 +1011,38 @@ int validate(const gclm_problem* p, const gclm_options* o) {
   if (p->camera_model < 0 || p->camera_model > 3) return GCLM_ERR_INVALID_ARGUMENT;  // :179-181
   if (!p->up_field && !p->latitude_field) return GCLM_ERR_INVALID_ARGUMENT;
   if (!p->camera_init || !p->gravity_init) return GCLM_ERR_INVALID_ARGUMENT;
-  if (p->width % 4 != 0) return GCLM_ERR_UNSUPPORTED;  // float4 rows (the CNN emits /32 sizes)
   if (o->num_steps < 0 || o->num_steps > 10000) return GCLM_ERR_INVALID_ARGUMENT;
   if (gclm_num_params(p->camera_model, p->estimate_gravity, p->estimate_focal) <= 0)
     return GCLM_ERR_INVALID_ARGUMENT;  // "No parameters to optimize" (:342)
-  auto mis = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) != 0; };
-  if (mis(p->up_field) || mis(p->latitude_field) || mis(p->up_confidence) || mis(p->latitude_confidence))
-    return GCLM_ERR_UNSUPPORTED;
-  if (((size_t)p->height * p->width) % 4 != 0) return GCLM_ERR_UNSUPPORTED;
   return GCLM_OK;
 }
+
+bool needs_repack(const gclm_problem* p) {
+  auto mis = [](const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15u) != 0; };
+  return p->width % 4 != 0 || mis(p->up_field) || mis(p->latitude_field) || mis(p->up_confidence) ||
+         mis(p->latitude_confidence);
+}
+inline int padded_width(int w) { return (w + 3) & ~3; }
 
 PassArgs make_args(gclm_handle* h, const gclm_problem* p, const gclm_options* o, const gclm_result* r,
                    const TileCfg& t, const Layout& L) {
   PassArgs a;
   memset(&a, 0, sizeof(a));
-  a.up = p->up_field;
-  a.lat = p->latitude_field ? reinterpret_cast<const float*>(static_cast<char*>(h->scratch) + L.sinlat) : nullptr;
-  a.uconf = p->up_field ? p->up_confidence : nullptr;
-  a.lconf = p->latitude_field ? p->latitude_confidence : nullptr;
-  a.B = p->batch; a.H = p->height; a.W = p->width;
+  const bool rp = needs_repack(p);
+  const int Wp = padded_width(p->width);
+  char* sb = static_cast<char*>(h->scratch);
+  if (rp) {  // all five planes live in scratch with pitch Wp (repack_kernel)
+    const size_t plane = (size_t)p->batch * p->height * Wp;
+    float* r = reinterpret_cast<float*>(sb + L.repack);
+    a.up = r; a.uconf = r + 2 * plane; a.lconf = r + 3 * plane;
+    a.lat = reinterpret_cast<const float*>(sb + L.sinlat);
+  } else {
+    a.up = p->up_field;
+    a.lat = p->latitude_field ? reinterpret_cast<const float*>(sb + L.sinlat) : nullptr;
+    a.uconf = p->up_field ? p->up_confidence : nullptr;
+    a.lconf = p->latitude_field ? p->latitude_confidence : nullptr;
+  }
+  a.B = p->batch; a.H = p->height; a.W = rp ? Wp : p->width; a.Wt = p->width;
   a.rows_per_tile = t.rows_per_tile; a.tiles_per_image = t.tiles_per_image; a.rsub = t.rsub;
   a.model = p->camera_model; a.num_steps = o->num_steps; a.early_stop = o->early_stop;
   a.fix_lambda = o->fix_lambda; a.spherical = o->use_spherical_manifold; a.log_focal = o->use_log_focal;
@@ -1028,6 +1068,16 @@ PassArgs make_args(gclm_handle* h, const gclm_problem* p, const gclm_options* o,
 
 // Enqueue sin(latitude_field) -> scratch (once per solve); a.lat already points at the scratch plane.
 void launch_sin_plane(gclm_handle* h, const gclm_problem* p, const PassArgs& a, cudaStream_t s) {
+  if (needs_repack(p)) {
+    const size_t total = (size_t)p->batch * p->height * a.W;
+    const unsigned blocks = (unsigned)std::min<size_t>((total + 255) / 256, (size_t)h->num_sms * 32);
+    repack_kernel<<<blocks, 256, 0, s>>>(p->batch, p->height, p->width, a.W, p->up_field, p->latitude_field,
+                                         p->up_confidence, p->latitude_confidence, const_cast<float*>(a.up),
+                                         const_cast<float*>(a.lat), const_cast<float*>(a.uconf),
+                                         const_cast<float*>(a.lconf));
+    h->launches++;
+    return;
+  }
   if (!p->latitude_field) return;
   const size_t n4 = (size_t)p->batch * p->height * p->width / 4;
   const unsigned blocks = (unsigned)std::min<size_t>((n4 + 255) / 256, (size_t)h->num_sms * 16);
@@ -1048,7 +1098,7 @@ const char* gclm_strerror(int status) {
     case GCLM_ERR_INVALID_ARGUMENT: return "invalid argument";
     case GCLM_ERR_CUDA: return "CUDA runtime error";
     case GCLM_ERR_OUT_OF_MEMORY: return "out of device memory";
-    case GCLM_ERR_UNSUPPORTED: return "unsupported configuration (width must be a multiple of 4, 16-byte aligned planes)";
+    case GCLM_ERR_UNSUPPORTED: return "unsupported configuration";
     case GCLM_ERR_NCCL: return "NCCL error";
     case GCLM_ERR_NO_DEVICE: return "no CUDA device";
     default: return "unknown status";
@@ -1102,7 +1152,7 @@ int gclm_destroy(gclm_handle* h) {
 int gclm_reserve(gclm_handle* h, int batch, int height, int width) {
   if (!h || batch <= 0 || height <= 0 || width <= 0) return GCLM_ERR_INVALID_ARGUMENT;
   CUDA_TRY(h, cudaSetDevice(h->device));
-  const Layout L = make_layout(batch, max_tiles_for(height, width), (size_t)height * width);
+  const Layout L = make_layout(batch, max_tiles_for(height, width), (size_t)height * padded_width(width), width % 4 != 0);
   return ensure_scratch(h, L.total);
 }
 
@@ -1116,10 +1166,10 @@ int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt
   if (prob->shared_intrinsics) return GCLM_ERR_INVALID_ARGUMENT;
   CUDA_TRY(h, cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-  const TileCfg t = tile_config(prob->batch, prob->height, prob->width, h->num_sms, opt->rows_per_tile,
+  const TileCfg t = tile_config(prob->batch, prob->height, padded_width(prob->width), h->num_sms, opt->rows_per_tile,
                                 max_warps_for(prob->camera_model, use_packed()));
   const Layout L = make_layout(prob->batch, std::max(t.tiles_per_image, max_tiles_for(prob->height, prob->width)),
-                               (size_t)prob->height * prob->width);
+                               (size_t)prob->height * padded_width(prob->width), needs_repack(prob));
   st = ensure_scratch(h, L.total);
   if (st != GCLM_OK) return st;
   PassArgs a = make_args(h, prob, opt, res, t, L);
@@ -1153,10 +1203,10 @@ int gclm_solve_shared(gclm_handle* h, const gclm_problem* prob, const gclm_optio
   }
   CUDA_TRY(h, cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-  const TileCfg t = tile_config(prob->batch, prob->height, prob->width, h->num_sms, opt->rows_per_tile,
+  const TileCfg t = tile_config(prob->batch, prob->height, padded_width(prob->width), h->num_sms, opt->rows_per_tile,
                                 max_warps_for(prob->camera_model, use_packed()));
   const Layout L = make_layout(prob->batch, std::max(t.tiles_per_image, max_tiles_for(prob->height, prob->width)),
-                               (size_t)prob->height * prob->width);
+                               (size_t)prob->height * padded_width(prob->width), needs_repack(prob));
   st = ensure_scratch(h, L.total);
   if (st != GCLM_OK) return st;
   PassArgs a = make_args(h, prob, opt, res, t, L);

@@ -72,7 +72,9 @@ typedef struct {
   int32_t camera_model; /* gclm_camera_model; LMOptimizer.set_camera_model (:173-187) */
 
   /* data["up_field"] (B,2,H,W), data["latitude_field"] (B,1,H,W) radians, contiguous NCHW fp32.
-   * Either may be NULL (lm_optimizer.py:265,269), not both. */
+   * Either may be NULL (lm_optimizer.py:265,269), not both.  Any H, W: rows that are a multiple of
+   * 4 pixels with 16-byte aligned planes are streamed in place, other shapes are repacked once per
+   * solve into padded scratch. */
   const float* up_field;
   const float* latitude_field;
   /* data["up_confidence"], data["latitude_confidence"] (B,H,W) or NULL (:295,307). */
