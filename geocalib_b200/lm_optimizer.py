@@ -30,7 +30,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from .camera import BaseCamera, camera_models, focal2fov, fov2focal, wrap_camera
+from .camera import BaseCamera, camera_models, focal2fov, wrap_camera
 from .engine import get_engine
 from .gravity import Gravity, wrap_gravity
 
