@@ -451,13 +451,26 @@ __global__ void shared_stop_kernel(const PassArgs a, const float* sum_in) {
 // CTA's prologue / reduction / solver epilogue overlaps the other's streaming loop:
 //   pinhole            : CTAs of <= 10 warps, <= 102 registers (96 used)
 //   distortion models  : packed accumulators need ~168 registers -> CTAs of <= 6 warps
+#ifndef GCLM_DIST_WARPS
+#define GCLM_DIST_WARPS 6
+#endif
+#ifndef GCLM_DIST_MINB
+#define GCLM_DIST_MINB 2
+#endif
+#ifndef GCLM_RING_UNROLL
+#define GCLM_RING_UNROLL 1
+#endif
+#ifndef GCLM_RING_UNROLL_DIST
+#define GCLM_RING_UNROLL_DIST 1
+#endif
 template <int MODEL, bool PACK>
 struct Tune {
-  static constexpr int MAX_WARPS_CTA = (MODEL == PINHOLE || !PACK) ? MAX_WARPS : 6;
-  static constexpr int MIN_BLOCKS = 2;
-  static constexpr int UNROLL = 2;
+  static constexpr int MAX_WARPS_CTA = (MODEL == PINHOLE || !PACK) ? MAX_WARPS : GCLM_DIST_WARPS;
+  static constexpr int MIN_BLOCKS = (MODEL == PINHOLE || !PACK) ? 2 : GCLM_DIST_MINB;
+  static constexpr int UNROLL = 2;  // direct-load loop (optional-input path)
+  static constexpr int RING_UNROLL = (MODEL == PINHOLE) ? GCLM_RING_UNROLL : GCLM_RING_UNROLL_DIST;
 };
-inline int max_warps_for(int model, bool pack) { return (model == PINHOLE || !pack) ? MAX_WARPS : 6; }
+inline int max_warps_for(int model, bool pack) { return (model == PINHOLE || !pack) ? MAX_WARPS : GCLM_DIST_WARPS; }
 
 template <int MODEL, bool GEN_D, bool FULL, bool PACK>
 __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MODEL, PACK>::MIN_BLOCKS)
@@ -633,7 +646,7 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
         cp_async_commit();
       }
       unsigned d = slot0;
-#pragma unroll 1
+#pragma unroll(Tune<MODEL, PACK>::RING_UNROLL)
       for (int y = y0; y < y1; ++y) {
         asm volatile("cp.async.wait_group %0;" ::"n"(RING_STAGES > 0 ? RING_STAGES - 1 : 0) : "memory");
         const float4 ox = lds128(d), oy = lds128(d + plane_stride), ol = lds128(d + 2u * plane_stride);

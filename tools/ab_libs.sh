@@ -1,7 +1,7 @@
 #!/bin/bash
 # tools/ab_libs.sh <log> <workload> <lib...> : bench each build of libgclm on the same box, twice (ABAB)
 LOG=$1; WL=$2; shift 2
-for rep in 1 2; do
+for rep in ${REPS:-1 2}; do
   for lib in "$@"; do
     echo -n "$WL $(basename $lib) rep$rep : " | tee -a $LOG
     GCLM_LIB=$PWD/$lib timeout 200 python bench.py --workload $WL --steps 4 --warmup 3 --no-e2e --no-cpu 2>&1 | tail -1 \
