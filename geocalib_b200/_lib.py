@@ -22,6 +22,7 @@ GCLM_OK = 0
 STOP_BATCH, STOP_PER_IMAGE = 0, 1
 STATUS_CHOLESKY_FAILED, STATUS_COV_SINGULAR, STATUS_NONFINITE = 1, 2, 4
 COMM_ID_BYTES = 128
+IPC_HANDLE_BYTES = 64
 
 CAMERA_MODEL_IDS = {"pinhole": 0, "simple_radial": 1, "radial": 2, "simple_divisional": 3}
 
@@ -74,6 +75,8 @@ SIGNATURES = {
     "gclm_comm_unique_id": (c_int, [c_void_p]),
     "gclm_comm_create": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]),
     "gclm_comm_destroy": (c_int, [c_void_p]),
+    "gclm_comm_p2p_export": (c_int, [c_void_p, c_void_p]),
+    "gclm_comm_p2p_attach": (c_int, [c_void_p, c_void_p]),
     "gclm_solve_host": (c_int, [c_void_p, POINTER(Problem), POINTER(Options), POINTER(Result), c_int]),
     "gclm_launch_count": (c_int64, [c_void_p]),
     "gclm_render_fields": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,

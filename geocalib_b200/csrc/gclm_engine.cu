@@ -369,8 +369,34 @@ __device__ __noinline__ void schur_image(const PassArgs& a, int b, const float* 
   out[31] = wg[0]; out[32] = wg[1];
 }
 
+// One-shot all-reduce over NVLink peer memory, fused into the reduction kernel: every rank stores its
+// 25 partial sums straight into a slot of EVERY peer's exchange buffer (P2P stores through the
+// NVSwitch), publishes a sequence number with system-scope release semantics, waits until all
+// peers' sequence numbers have arrived in its own buffer and adds the contributions in rank order
+// (bit-identical on every rank).  Two slots (seq & 1): a rank can never be two exchanges ahead.
+constexpr int P2P_MAX_RANKS = 8;
+struct P2PBuf {  // one per rank, mapped into every peer with CUDA IPC
+  float data[2][P2P_MAX_RANKS][32];
+  unsigned flag[2][P2P_MAX_RANKS];
+};
+struct P2PArgs {
+  P2PBuf* peer[P2P_MAX_RANKS];  // peer[r] = rank r's buffer as seen from this device (peer[rank] = local)
+  int world, rank;
+  unsigned seq;  // > 0, identical on all ranks for this exchange; world == 0 disables the exchange
+};
+
+__device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
+  asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 // Sum the per-image Schur partials of this rank in a fixed order -> sum_out[SCHUR_NSUM].
-__global__ void __launch_bounds__(1024) shared_reduce_kernel(const __grid_constant__ PassArgs a, float* sum_out) {
+__global__ void __launch_bounds__(1024) shared_reduce_kernel(const __grid_constant__ PassArgs a, float* sum_out,
+                                                            const __grid_constant__ P2PArgs pp) {
   __shared__ float s[32][SCHUR_NSUM];
   if (*(volatile int*)&a.ctrl->stop) return;
   const int j = threadIdx.x & 31, grp = threadIdx.x >> 5;
@@ -380,10 +406,35 @@ __global__ void __launch_bounds__(1024) shared_reduce_kernel(const __grid_consta
     s[grp][j] = acc;
   }
   __syncthreads();
+  float mine = 0.f;
+  if (threadIdx.x < SCHUR_NSUM) {
+    for (int g = 0; g < 32; g++) mine += s[g][threadIdx.x];
+    if (pp.world <= 1) sum_out[threadIdx.x] = mine;
+  }
+  if (pp.world <= 1) return;
+  // ---- exchange (warp 0 only) ----
+  if (threadIdx.x >= 32) return;
+  const int slot = pp.seq & 1u;
+  if (threadIdx.x < SCHUR_NSUM)
+    for (int r = 0; r < pp.world; r++) pp.peer[r]->data[slot][pp.rank][threadIdx.x] = mine;  // P2P stores
+  __threadfence_system();
+  __syncwarp();
+  if (threadIdx.x < pp.world) st_release_sys(&pp.peer[threadIdx.x]->flag[slot][pp.rank], pp.seq);
+  bool ok = true;
+  if (threadIdx.x < pp.world) {  // wait for rank `threadIdx.x`'s contribution in MY buffer (bounded)
+    const unsigned* f = &pp.peer[pp.rank]->flag[slot][threadIdx.x];
+    unsigned spins = 0;
+    while (ld_acquire_sys(f) != pp.seq) {
+      if (++spins > (1u << 27)) { ok = false; break; }
+      __nanosleep(64);
+    }
+  }
+  ok = __all_sync(0xffffffffu, ok);
   if (threadIdx.x < SCHUR_NSUM) {
     float acc = 0.f;
-    for (int g = 0; g < 32; g++) acc += s[g][threadIdx.x];
-    sum_out[threadIdx.x] = acc;
+    const P2PBuf* me = pp.peer[pp.rank];
+    for (int r = 0; r < pp.world; r++) acc += *(volatile const float*)&me->data[slot][r][threadIdx.x];
+    sum_out[threadIdx.x] = ok ? acc : __int_as_float(0x7fc00000);  // a lost peer poisons the step, never hangs
   }
 }
 
@@ -898,8 +949,13 @@ static NcclApi* nccl_api() {
 }
 
 struct gclm_comm {
-  void* comm = nullptr;
+  void* comm = nullptr;  // ncclComm_t
   int world = 1, rank = 0, device = 0;
+  // peer-memory exchange (CUDA IPC): local buffer + every peer's buffer mapped here
+  gclm::P2PBuf* local = nullptr;
+  gclm::P2PBuf* peer[gclm::P2P_MAX_RANKS] = {nullptr};
+  bool p2p_ready = false;
+  unsigned seq = 0;
 };
 
 #define CUDA_TRY(h, expr)                                                                  \
@@ -1210,9 +1266,9 @@ int gclm_solve_shared(gclm_handle* h, const gclm_problem* prob, const gclm_optio
   if (st != GCLM_OK) return st;
   if (!prob->shared_intrinsics) return GCLM_ERR_INVALID_ARGUMENT;
   NcclApi* nccl = nullptr;
-  if (comm && comm->world > 1) {
+  if (comm && comm->world > 1 && !comm->p2p_ready) {
     nccl = nccl_api();
-    if (!nccl) return GCLM_ERR_NCCL;
+    if (!nccl || !comm->comm) return GCLM_ERR_NCCL;
   }
   CUDA_TRY(h, cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
@@ -1235,8 +1291,15 @@ int gclm_solve_shared(gclm_handle* h, const gclm_problem* prob, const gclm_optio
   for (int it = 0; it < opt->num_steps; it++) {
     a.pass = it; a.is_final = 0;
     launch_pass(a, !opt->use_log_focal, full, grid, block, s);
-    shared_reduce_kernel<<<1, 1024, 0, s>>>(a, sums);
-    if (nccl) {
+    P2PArgs pp;
+    memset(&pp, 0, sizeof(pp));
+    const bool p2p = comm && comm->world > 1 && comm->p2p_ready;
+    if (p2p) {
+      pp.world = comm->world; pp.rank = comm->rank; pp.seq = ++comm->seq;
+      for (int r = 0; r < comm->world; r++) pp.peer[r] = comm->peer[r];
+    }
+    shared_reduce_kernel<<<1, 1024, 0, s>>>(a, sums, pp);
+    if (nccl && !p2p) {
       const int rc = nccl->all_reduce(sums, sums, SCHUR_NSUM, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm->comm, s);
       if (rc != 0) {
         snprintf(h->last_error, sizeof(h->last_error), "ncclAllReduce: %s",
@@ -1288,9 +1351,49 @@ int gclm_comm_create(const void* unique_id, int world_size, int rank, int device
 
 int gclm_comm_destroy(gclm_comm* c) {
   if (!c) return GCLM_OK;
+  cudaSetDevice(c->device);
+  for (int r = 0; r < c->world && r < P2P_MAX_RANKS; r++)
+    if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+  if (c->local) cudaFree(c->local);
   NcclApi* nccl = nccl_api();
   if (nccl && c->comm) nccl->comm_destroy(c->comm);
   delete c;
+  return GCLM_OK;
+}
+
+int gclm_comm_p2p_export(gclm_comm* c, void* handle_out) {
+  if (!c || !handle_out) return GCLM_ERR_INVALID_ARGUMENT;
+  if (c->world > P2P_MAX_RANKS) return GCLM_ERR_UNSUPPORTED;
+  static_assert(sizeof(cudaIpcMemHandle_t) <= GCLM_IPC_HANDLE_BYTES, "IPC handle size");
+  if (cudaSetDevice(c->device) != cudaSuccess) return GCLM_ERR_CUDA;
+  if (!c->local) {
+    if (cudaMalloc(reinterpret_cast<void**>(&c->local), sizeof(P2PBuf)) != cudaSuccess) return GCLM_ERR_OUT_OF_MEMORY;
+    if (cudaMemset(c->local, 0, sizeof(P2PBuf)) != cudaSuccess) return GCLM_ERR_CUDA;
+    if (cudaDeviceSynchronize() != cudaSuccess) return GCLM_ERR_CUDA;
+  }
+  cudaIpcMemHandle_t hnd;
+  if (cudaIpcGetMemHandle(&hnd, c->local) != cudaSuccess) return GCLM_ERR_CUDA;
+  memset(handle_out, 0, GCLM_IPC_HANDLE_BYTES);
+  memcpy(handle_out, &hnd, sizeof(hnd));
+  return GCLM_OK;
+}
+
+int gclm_comm_p2p_attach(gclm_comm* c, const void* handles) {
+  if (!c || !handles || !c->local) return GCLM_ERR_INVALID_ARGUMENT;
+  if (c->world > P2P_MAX_RANKS) return GCLM_ERR_UNSUPPORTED;
+  if (cudaSetDevice(c->device) != cudaSuccess) return GCLM_ERR_CUDA;
+  for (int r = 0; r < c->world; r++) {
+    if (r == c->rank) { c->peer[r] = c->local; continue; }
+    cudaIpcMemHandle_t hnd;
+    memcpy(&hnd, static_cast<const char*>(handles) + (size_t)r * GCLM_IPC_HANDLE_BYTES, sizeof(hnd));
+    void* ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, hnd, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      return GCLM_ERR_CUDA;
+    }
+    c->peer[r] = static_cast<P2PBuf*>(ptr);
+  }
+  c->p2p_ready = true;
   return GCLM_OK;
 }
 

@@ -12,6 +12,7 @@ C ABI needs (`gclm_comm_create`), using torch.distributed only to broadcast the 
 from __future__ import annotations
 
 import ctypes
+import os
 from typing import Tuple
 
 import numpy as np
@@ -47,6 +48,7 @@ class Comm:
 
     def __init__(self, handle: ctypes.c_void_p, world: int, rank: int):
         self.handle, self.world, self.rank = handle, world, rank
+        self.p2p = False
 
     def __del__(self):
         try:
@@ -57,7 +59,7 @@ class Comm:
             pass
 
 
-def make_comm(device: torch.device) -> Comm:
+def make_comm(device: torch.device, p2p: bool = None) -> Comm:
     """Create the engine's communicator over the ranks of the default process group."""
     import torch.distributed as dist
 
@@ -70,7 +72,31 @@ def make_comm(device: torch.device) -> Comm:
     h = ctypes.c_void_p()
     idx = device.index if device.index is not None else torch.cuda.current_device()
     _lib.check(lib.gclm_comm_create(uid, world, rank, idx, ctypes.byref(h)), "gclm_comm_create")
-    return Comm(h, world, rank)
+    comm = Comm(h, world, rank)
+    if p2p is None:
+        p2p = os.environ.get("GCLM_P2P", "1") != "0"
+    if p2p and world <= 8:
+        attach_peer_memory(comm, device)
+    return comm
+
+
+def attach_peer_memory(comm: Comm, device: torch.device) -> None:
+    """Exchange CUDA-IPC handles of the per-rank exchange buffers so that the per-step reduction
+    kernel can do its all-reduce with direct NVLink stores (include/gclm.h: gclm_comm_p2p_*)."""
+    import torch.distributed as dist
+
+    lib = _lib.load()
+    mine = (ctypes.c_char * _lib.IPC_HANDLE_BYTES)()
+    _lib.check(lib.gclm_comm_p2p_export(comm.handle, mine), "gclm_comm_p2p_export")
+    t = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).clone()
+    on_gpu = dist.get_backend() == "nccl"
+    t = t.to(device) if on_gpu else t
+    gathered = [torch.empty_like(t) for _ in range(comm.world)]
+    dist.all_gather(gathered, t)
+    blob = b"".join(bytes(g.cpu().numpy().tobytes()) for g in gathered)
+    _lib.check(lib.gclm_comm_p2p_attach(comm.handle, blob), "gclm_comm_p2p_attach")
+    dist.barrier()  # every buffer is zeroed and mapped everywhere before the first exchange
+    comm.p2p = True
 
 
 # ---- host-side mirror of the device Schur reduction (csrc: schur_image / shared_update_kernel) ----

@@ -170,6 +170,17 @@ int gclm_solve_shared(gclm_handle* h, const gclm_problem* prob, const gclm_optio
 int gclm_comm_unique_id(void* id_out);
 int gclm_comm_create(const void* unique_id, int world_size, int rank, int device, gclm_comm** out);
 int gclm_comm_destroy(gclm_comm* c);
+/*
+ * Optional peer-memory exchange (one node, NVLink / NVSwitch): instead of an NCCL all-reduce, the
+ * per-step reduction kernel stores its partial sums directly into every peer's exchange buffer and
+ * waits for the peers' sums in its own -- one kernel does the reduction AND the collective.
+ * Each rank exports a CUDA-IPC handle of its buffer (GCLM_IPC_HANDLE_BYTES bytes); the host
+ * framework all-gathers the handles (rank order) and every rank attaches them, followed by a
+ * barrier.  Without these two calls gclm_solve_shared uses NCCL.  At most 8 ranks.
+ */
+#define GCLM_IPC_HANDLE_BYTES 64
+int gclm_comm_p2p_export(gclm_comm* c, void* handle_out);
+int gclm_comm_p2p_attach(gclm_comm* c, const void* handles /* world x GCLM_IPC_HANDLE_BYTES */);
 
 /*
  * Host-buffer convenience path (end-to-end measurement; the call a non-CUDA host makes):

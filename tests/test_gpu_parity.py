@@ -466,9 +466,18 @@ def _two_gpu_worker(rank, world, port, q):
         with torch.no_grad():
             full = opt(f)  # single-GPU answer over all B images
             lo, hi = shard_range(B, world, rank)
-            opt.comm = make_comm(d)
-            part = opt({k: v[lo:hi].contiguous() for k, v in f.items()})
+            shard = {k: v[lo:hi].contiguous() for k, v in f.items()}
+            opt.comm = make_comm(d, p2p=False)  # NCCL all-reduce per LM step
+            assert not opt.comm.p2p
+            part_nccl = opt(shard)
+            opt.comm = make_comm(d, p2p=True)   # reduction + exchange fused over NVLink peer memory
+            assert opt.comm.p2p
+            part = opt(shard)
+            part2 = opt(shard)                  # sequence numbers / slots keep working across calls
         torch.cuda.synchronize()
+        assert torch.equal(part["camera"]._data, part2["camera"]._data)
+        assert torch.equal(part["camera"]._data, part_nccl["camera"]._data)  # same sums, same order
+        assert torch.equal(part["gravity"]._data, part_nccl["gravity"]._data)
         q.put((rank, full["camera"]._data.cpu().numpy(), full["gravity"]._data.cpu().numpy(),
                part["camera"]._data.cpu().numpy(), part["gravity"]._data.cpu().numpy(), lo, hi))
     finally:
@@ -476,7 +485,8 @@ def _two_gpu_worker(rank, world, port, q):
 
 
 def test_shared_intrinsics_two_gpus(dev):
-    """Images sharded over 2 ranks + one NCCL all-reduce per LM step == the single-GPU solve."""
+    """Images sharded over 2 ranks + one all-reduce per LM step (NCCL, and the fused peer-memory
+    exchange) == the single-GPU solve."""
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
     import socket
