@@ -77,6 +77,7 @@ SIGNATURES = {
     "gclm_comm_destroy": (c_int, [c_void_p]),
     "gclm_comm_p2p_export": (c_int, [c_void_p, c_void_p]),
     "gclm_comm_p2p_attach": (c_int, [c_void_p, c_void_p]),
+    "gclm_comm_p2p_disable": (c_int, [c_void_p]),
     "gclm_solve_host": (c_int, [c_void_p, POINTER(Problem), POINTER(Options), POINTER(Result), c_int]),
     "gclm_launch_count": (c_int64, [c_void_p]),
     "gclm_render_fields": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,

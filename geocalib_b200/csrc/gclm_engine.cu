@@ -1378,6 +1378,12 @@ int gclm_comm_p2p_export(gclm_comm* c, void* handle_out) {
   return GCLM_OK;
 }
 
+int gclm_comm_p2p_disable(gclm_comm* c) {
+  if (!c) return GCLM_ERR_INVALID_ARGUMENT;
+  c->p2p_ready = false;
+  return GCLM_OK;
+}
+
 int gclm_comm_p2p_attach(gclm_comm* c, const void* handles) {
   if (!c || !handles || !c->local) return GCLM_ERR_INVALID_ARGUMENT;
   if (c->world > P2P_MAX_RANKS) return GCLM_ERR_UNSUPPORTED;

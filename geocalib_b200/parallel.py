@@ -80,23 +80,35 @@ def make_comm(device: torch.device, p2p: bool = None) -> Comm:
     return comm
 
 
-def attach_peer_memory(comm: Comm, device: torch.device) -> None:
+def attach_peer_memory(comm: Comm, device: torch.device) -> bool:
     """Exchange CUDA-IPC handles of the per-rank exchange buffers so that the per-step reduction
-    kernel can do its all-reduce with direct NVLink stores (include/gclm.h: gclm_comm_p2p_*)."""
+    kernel can do its all-reduce with direct NVLink stores (include/gclm.h: gclm_comm_p2p_*).
+
+    Collective over the default group.  If ANY rank cannot export / map the buffers (no peer access,
+    IPC disabled in the container, ...) every rank keeps the NCCL path -- the decision is agreed with
+    a MIN all-reduce so that no rank waits on a peer that never writes."""
     import torch.distributed as dist
 
     lib = _lib.load()
-    mine = (ctypes.c_char * _lib.IPC_HANDLE_BYTES)()
-    _lib.check(lib.gclm_comm_p2p_export(comm.handle, mine), "gclm_comm_p2p_export")
-    t = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).clone()
     on_gpu = dist.get_backend() == "nccl"
+    mine = (ctypes.c_char * _lib.IPC_HANDLE_BYTES)()
+    ok = lib.gclm_comm_p2p_export(comm.handle, mine) == _lib.GCLM_OK
+    t = torch.frombuffer(bytearray(mine.raw), dtype=torch.uint8).clone()
     t = t.to(device) if on_gpu else t
     gathered = [torch.empty_like(t) for _ in range(comm.world)]
     dist.all_gather(gathered, t)
-    blob = b"".join(bytes(g.cpu().numpy().tobytes()) for g in gathered)
-    _lib.check(lib.gclm_comm_p2p_attach(comm.handle, blob), "gclm_comm_p2p_attach")
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device if on_gpu else "cpu")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 1:
+        blob = b"".join(bytes(g.cpu().numpy().tobytes()) for g in gathered)
+        ok = lib.gclm_comm_p2p_attach(comm.handle, blob) == _lib.GCLM_OK
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=device if on_gpu else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    comm.p2p = int(flag.item()) == 1
+    if not comm.p2p:
+        _lib.check(lib.gclm_comm_p2p_disable(comm.handle), "gclm_comm_p2p_disable")
     dist.barrier()  # every buffer is zeroed and mapped everywhere before the first exchange
-    comm.p2p = True
+    return comm.p2p
 
 
 # ---- host-side mirror of the device Schur reduction (csrc: schur_image / shared_update_kernel) ----

@@ -181,6 +181,8 @@ int gclm_comm_destroy(gclm_comm* c);
 #define GCLM_IPC_HANDLE_BYTES 64
 int gclm_comm_p2p_export(gclm_comm* c, void* handle_out);
 int gclm_comm_p2p_attach(gclm_comm* c, const void* handles /* world x GCLM_IPC_HANDLE_BYTES */);
+/* Back to NCCL for this communicator (call on every rank, e.g. when one rank failed to attach). */
+int gclm_comm_p2p_disable(gclm_comm* c);
 
 /*
  * Host-buffer convenience path (end-to-end measurement; the call a non-CUDA host makes):

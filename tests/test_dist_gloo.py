@@ -75,10 +75,13 @@ def test_schur_allreduce_equals_dense_arrow_system(case):
     procs = [ctx.Process(target=_worker, args=(r, world, port, case, q)) for r in range(world)]
     for p in procs:
         p.start()
+    for p in procs:  # join first: a crashed worker must fail the test, not hang it on q.get()
+        p.join(120)
+        if p.is_alive():
+            p.terminate()
+        assert p.exitcode == 0, f"gloo worker exited with {p.exitcode}"
+    assert not q.empty()
     gathered = q.get()
-    for p in procs:
-        p.join(60)
-        assert p.exitcode == 0
     # both ranks solved the same shared step
     np.testing.assert_array_equal(gathered[0][0], gathered[1][0])
     dc = gathered[0][0]

@@ -501,10 +501,12 @@ def test_shared_intrinsics_two_gpus(dev):
     procs = [ctx.Process(target=_two_gpu_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
+    for p in procs:  # join first: a crashed worker must fail the test, not hang it on q.get()
+        p.join(240)
+        if p.is_alive():
+            p.terminate()
+        assert p.exitcode == 0, f"worker exited with {p.exitcode}"
     got = [q.get() for _ in range(2)]
-    for p in procs:
-        p.join(120)
-        assert p.exitcode == 0
     for rank, cam_full, g_full, cam_part, g_part, lo, hi in got:
         np.testing.assert_allclose(cam_part[:, 3], cam_full[lo:hi, 3], rtol=2e-6)
         np.testing.assert_allclose(g_part, g_full[lo:hi], atol=2e-6)
