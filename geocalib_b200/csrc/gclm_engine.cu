@@ -15,6 +15,7 @@
 //   Hessian in the (roll,pitch,f,k) basis for the covariance (lm_optimizer.py:632-636, 463-516).
 //
 // Passes per solve: num_steps + 1 (the reference makes 2*num_steps + 2 logical passes).
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdint.h>
@@ -118,6 +119,19 @@ __device__ __forceinline__ bool mbar_wait(unsigned bar, unsigned parity) {
   }
   return false;
 }
+
+#ifdef GCLM_TMA2D
+#ifndef GCLM_TMA_ROWS
+#define GCLM_TMA_ROWS 2
+#endif
+constexpr int TMA_ROWS = GCLM_TMA_ROWS;  // image rows per TMA box (box = 128 pixels x TMA_ROWS rows)
+constexpr int TMA_STAGES = 2;            // boxes in flight per warp and plane
+struct TmaMaps { CUtensorMap up, lat, uconf, lconf; };  // 2-D views (width W) of the planes
+__device__ __forceinline__ void tma_box_g2s(unsigned dst, const CUtensorMap* map, int x, int y, unsigned bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+               ::"r"(dst), "l"(reinterpret_cast<unsigned long long>(map)), "r"(x), "r"(y), "r"(bar) : "memory");
+}
+#endif
 
 __device__ __forceinline__ float4 lds128(unsigned addr) {
   float4 r;
@@ -525,7 +539,11 @@ inline int max_warps_for(int model, bool pack) { return (model == PINHOLE || !pa
 
 template <int MODEL, bool GEN_D, bool FULL, bool PACK>
 __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MODEL, PACK>::MIN_BLOCKS)
+#ifdef GCLM_TMA2D
+    lm_pass_kernel(const __grid_constant__ PassArgs a, const __grid_constant__ TmaMaps tm) {
+#else
     lm_pass_kernel(const __grid_constant__ PassArgs a) {
+#endif
   constexpr int NACC = Dims<MODEL>::NACC;
   using V = typename std::conditional<PACK, f2, float>::type;  // 2 pixels per op when packed
   const int b = blockIdx.x / a.tiles_per_image;
@@ -550,7 +568,11 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
   const float inv_up2 = 1.f / (a.up_scale * a.up_scale), inv_lat2 = 1.f / (a.lat_scale * a.lat_scale);
 
   extern __shared__ __align__(16) unsigned char dyn_smem[];
+#ifdef GCLM_TMA2D
+  const unsigned smem_u32 = ((unsigned)__cvta_generic_to_shared(dyn_smem) + 127u) & ~127u;  // TMA boxes need 128 B
+#else
   const unsigned smem_u32 = (unsigned)__cvta_generic_to_shared(dyn_smem);
+#endif
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   const int W = a.W, H = a.H;
   const size_t N = (size_t)H * W;
@@ -563,6 +585,19 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
 #pragma unroll
   for (int i = 0; i < NACC; i++) acc[i] = splat<V>(0.f);
 
+#ifdef GCLM_TMA2D
+  unsigned tma_it = 0;  // stages issued == consumed so far by this warp (ring position / phase)
+  const unsigned t2_wbase = smem_u32 + (unsigned)warp * (TMA_STAGES * 5u * TMA_ROWS * 512u);
+  const unsigned t2_bars = smem_u32 + (unsigned)nwarps * (TMA_STAGES * 5u * TMA_ROWS * 512u) + (unsigned)warp * (TMA_STAGES * 8u);
+  if (FULL) {
+    if (lane == 0) {
+      for (int k = 0; k < TMA_STAGES; k++) mbar_init(t2_bars + k * 8u, 1u);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncwarp();
+  }
+#endif
 #ifdef GCLM_TMA
   unsigned tma_it = 0;  // rows issued == rows consumed so far by this warp (ring position / phase)
   if (FULL && RING_STAGES > 0) {
@@ -579,7 +614,7 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
     const int strip = job % NS, sub = job / NS;
     const int x0 = (strip << 7) + (lane << 2);
     const int y0 = yt0 + sub * RJ, y1 = min(yt1, y0 + RJ);
-#ifdef GCLM_TMA
+#if defined(GCLM_TMA) || defined(GCLM_TMA2D)
     if (!FULL && x0 >= W) continue;
 #else
     if (x0 >= W) continue;  // W % 4 == 0 is enforced on the host
@@ -634,6 +669,53 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
         pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[3], v, ox.w, oy.w, sl3, cu.w, cl.w, inv_up2, inv_lat2, acc);
       }
     };
+#ifdef GCLM_TMA2D
+    if constexpr (FULL) {
+      // ---- 2-D TMA ring: lane 0 issues ONE tensor copy per plane per stage (box = this warp's
+      // 128-pixel strip x TMA_ROWS rows, cp.async.bulk.tensor.2d, SASS UTMALDG), TMA_STAGES stages
+      // ahead; completion on a per-stage mbarrier; every lane reads its float4 with LDS.128.
+      constexpr unsigned STAGE_BYTES = 5u * TMA_ROWS * 512u, PLANE_BYTES = TMA_ROWS * 512u;  // smem slots
+      const unsigned row_pitch = (unsigned)min(128, W) * 4u;            // dense box rows in shared memory
+      const unsigned tx_bytes = 5u * TMA_ROWS * row_pitch;              // bytes one stage delivers
+      const int nst = (y1 - y0 + TMA_ROWS - 1) / TMA_ROWS;
+      const int xs = strip << 7;
+      auto issue = [&](unsigned st, int yy) {  // lane 0 only
+        const unsigned d = t2_wbase + st * STAGE_BYTES, bar = t2_bars + st * 8u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_expect_tx(bar, tx_bytes);
+        tma_box_g2s(d, &tm.up, xs, (b * 2) * H + yy, bar);
+        tma_box_g2s(d + PLANE_BYTES, &tm.up, xs, (b * 2 + 1) * H + yy, bar);
+        tma_box_g2s(d + 2u * PLANE_BYTES, &tm.lat, xs, b * H + yy, bar);
+        tma_box_g2s(d + 3u * PLANE_BYTES, &tm.uconf, xs, b * H + yy, bar);
+        tma_box_g2s(d + 4u * PLANE_BYTES, &tm.lconf, xs, b * H + yy, bar);
+      };
+      if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < TMA_STAGES; k++)
+          if (k < nst) issue((tma_it + k) % TMA_STAGES, y0 + k * TMA_ROWS);
+      }
+      const bool active = x0 < W;
+#pragma unroll 1
+      for (int i = 0; i < nst; ++i) {
+        const unsigned st = tma_it % TMA_STAGES, par = (tma_it / TMA_STAGES) & 1u;
+        if (!mbar_wait(t2_bars + st * 8u, par)) a.flags[b] |= GCLM_STATUS_NONFINITE;
+        const unsigned d0 = t2_wbase + st * STAGE_BYTES + (unsigned)lane * 16u;
+#pragma unroll
+        for (int r = 0; r < TMA_ROWS; r++) {
+          const int y = y0 + i * TMA_ROWS + r;
+          if (active && y < y1) {
+            const unsigned d = d0 + r * row_pitch;
+            const float4 ox = lds128(d), oy = lds128(d + PLANE_BYTES), ol = lds128(d + 2u * PLANE_BYTES);
+            const float4 cu = lds128(d + 3u * PLANE_BYTES), cl = lds128(d + 4u * PLANE_BYTES);
+            row(ox, oy, ol, cu, cl, y);
+          }
+        }
+        __syncwarp();  // every lane is done with this stage before it is refilled
+        if (lane == 0 && i + TMA_STAGES < nst) issue(st, y0 + (i + TMA_STAGES) * TMA_ROWS);
+        ++tma_it;
+      }
+    } else
+#endif
 #ifdef GCLM_TMA
     if constexpr (FULL && RING_STAGES > 0) {
       // ---- TMA ring: lane 0 of the warp issues ONE bulk copy per plane per row (the strip's 512 B,
@@ -1027,6 +1109,36 @@ int max_tiles_for(int H, int W) {
   return (H + 3) / 4 + 1;  // smallest auto tile is 4 rows (rsub == 1)
 }
 
+#ifdef GCLM_TMA2D
+TmaMaps g_maps;  // tensor maps of the current solve (a handle is single-threaded by contract)
+
+// 2-D tensor maps (width W, all rows of all images of a plane stacked) for the TMA build.
+bool encode_maps(const PassArgs& a) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn enc = nullptr;
+  if (!enc) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) != cudaSuccess || !fn) return false;
+    enc = reinterpret_cast<encode_fn>(fn);
+  }
+  auto one = [&](CUtensorMap* m, const float* base, size_t rows) {
+    cuuint64_t dims[2] = {(cuuint64_t)a.W, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)a.W * 4};
+    cuuint32_t box[2] = {(cuuint32_t)std::min(128, a.W), (cuuint32_t)TMA_ROWS};
+    cuuint32_t estr[2] = {1, 1};
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  const size_t rows = (size_t)a.B * a.H;
+  return one(&g_maps.up, a.up, rows * 2) && one(&g_maps.lat, a.lat, rows) && one(&g_maps.uconf, a.uconf, rows) &&
+         one(&g_maps.lconf, a.lconf, rows);
+}
+#endif
+
 template <int MODEL, bool GEN_D, bool FULL, bool PACK>
 void launch_one(const PassArgs& a, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
   static size_t configured = 0;  // opt in to > 48 KB of dynamic shared memory once per instantiation
@@ -1034,12 +1146,21 @@ void launch_one(const PassArgs& a, dim3 grid, dim3 block, size_t smem, cudaStrea
     cudaFuncSetAttribute(lm_pass_kernel<MODEL, GEN_D, FULL, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
+#ifdef GCLM_TMA2D
+  lm_pass_kernel<MODEL, GEN_D, FULL, PACK><<<grid, block, smem, s>>>(a, g_maps);
+#else
   lm_pass_kernel<MODEL, GEN_D, FULL, PACK><<<grid, block, smem, s>>>(a);
+#endif
 }
 
 template <int MODEL, bool PACK>
 void launch_pass_model(const PassArgs& a, bool gen_d, bool full, dim3 grid, dim3 block, cudaStream_t s) {
+#ifdef GCLM_TMA2D
+  const size_t smem = full ? (size_t)(block.x / 32) * (TMA_STAGES * 5 * TMA_ROWS * 512 + TMA_STAGES * 8) + 128 : 0;
+  if (full && !encode_maps(a)) return;  // leaves the sticky error for cudaGetLastError-less callers: results stay unset
+#else
   const size_t smem = full ? (size_t)RING_STAGES * 5 * block.x * 16 + (size_t)(block.x / 32) * RING_STAGES * 8 : 0;
+#endif
   if (gen_d) {
     if (full) launch_one<MODEL, true, true, PACK>(a, grid, block, smem, s);
     else launch_one<MODEL, true, false, PACK>(a, grid, block, 0, s);
