@@ -512,15 +512,23 @@ __global__ void shared_stop_kernel(const PassArgs a, const float* sum_in) {
 // ---------------------------------------------------------------------------------------------
 // the fused pass kernel
 // ---------------------------------------------------------------------------------------------
-// Register / occupancy budget per instantiation.  Two resident CTAs per SM everywhere, so that one
-// CTA's prologue / reduction / solver epilogue overlaps the other's streaming loop:
-//   pinhole            : CTAs of <= 10 warps, <= 102 registers (96 used)
-//   distortion models  : packed accumulators need ~168 registers -> CTAs of <= 6 warps
+// Register / occupancy budget per instantiation.  The pass is FP32-issue bound, not latency bound
+// (the cp.async ring hides HBM), so registers for the instruction scheduler beat resident warps;
+// at least two CTAs per SM so that one CTA's prologue / reduction / solver epilogue overlaps the
+// others' streaming loops.  A/B on B200 (profiles/r1_ab_cta_shapes.txt):
+//   pinhole            : 2 CTAs x 8 warps, 128 registers (126 used; 10 warps at 96 was 6 % slower)
+//   distortion models  : 3 CTAs x 4 warps, 168 registers (packed accumulators need ~165)
+#ifndef GCLM_PIN_WARPS
+#define GCLM_PIN_WARPS 8
+#endif
+#ifndef GCLM_PIN_MINB
+#define GCLM_PIN_MINB 2
+#endif
 #ifndef GCLM_DIST_WARPS
-#define GCLM_DIST_WARPS 6
+#define GCLM_DIST_WARPS 4
 #endif
 #ifndef GCLM_DIST_MINB
-#define GCLM_DIST_MINB 2
+#define GCLM_DIST_MINB 3
 #endif
 #ifndef GCLM_RING_UNROLL
 #define GCLM_RING_UNROLL 1
@@ -530,12 +538,12 @@ __global__ void shared_stop_kernel(const PassArgs a, const float* sum_in) {
 #endif
 template <int MODEL, bool PACK>
 struct Tune {
-  static constexpr int MAX_WARPS_CTA = (MODEL == PINHOLE || !PACK) ? MAX_WARPS : GCLM_DIST_WARPS;
-  static constexpr int MIN_BLOCKS = (MODEL == PINHOLE || !PACK) ? 2 : GCLM_DIST_MINB;
+  static constexpr int MAX_WARPS_CTA = (MODEL == PINHOLE || !PACK) ? GCLM_PIN_WARPS : GCLM_DIST_WARPS;
+  static constexpr int MIN_BLOCKS = (MODEL == PINHOLE || !PACK) ? GCLM_PIN_MINB : GCLM_DIST_MINB;
   static constexpr int UNROLL = 2;  // direct-load loop (optional-input path)
   static constexpr int RING_UNROLL = (MODEL == PINHOLE) ? GCLM_RING_UNROLL : GCLM_RING_UNROLL_DIST;
 };
-inline int max_warps_for(int model, bool pack) { return (model == PINHOLE || !pack) ? MAX_WARPS : GCLM_DIST_WARPS; }
+inline int max_warps_for(int model, bool pack) { return (model == PINHOLE || !pack) ? GCLM_PIN_WARPS : GCLM_DIST_WARPS; }
 
 template <int MODEL, bool GEN_D, bool FULL, bool PACK>
 __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MODEL, PACK>::MIN_BLOCKS)
@@ -1058,14 +1066,22 @@ struct Layout {  // carve the scratch buffer
 struct TileCfg { int nwarps, rsub, rows_per_tile, tiles_per_image; };
 
 TileCfg tile_config(int B, int H, int W, int num_sms, int rows_override, int max_warps) {
+  // A tile is a band of rows of one image, one CTA each.  It is cut into NS 128-pixel column strips
+  // x rsub row bands = NS * rsub jobs; warp w walks jobs w, w + nwarps, ...  rsub is the smallest
+  // count that gives every warp the same number of jobs (NS / gcd), so all max_warps warps are busy
+  // for any image width.
   TileCfg t;
-  const int NS = (W + 127) / 128;  // 128-pixel column strips, one warp each
-  if (NS <= max_warps) { t.rsub = std::max(1, max_warps / NS); t.nwarps = NS * t.rsub; }
-  else {  // more strips than warps: every warp walks NS / nwarps strips (nwarps divides NS)
-    t.rsub = 1; t.nwarps = 1;
-    for (int d = 1; d <= max_warps; d++) if (NS % d == 0) t.nwarps = d;
-  }
-  int rj = 120;  // rows walked by one warp per tile (long tiles amortise the CTA prologue/epilogue)
+  const int NS = (W + 127) / 128;
+  int g = NS, r = max_warps;
+  while (r) { const int q = g % r; g = r; r = q; }  // gcd(NS, max_warps)
+  t.nwarps = max_warps;
+  t.rsub = max_warps / g;
+  const int jobs_per_warp = NS / g;
+  // ~120 rows walked by a warp per tile (long tiles amortise the CTA prologue/epilogue), tiles of
+  // equal height
+  const int rj_target = std::max(4, 120 / jobs_per_warp);
+  const int tiles = std::max(1, (H + rj_target * t.rsub / 2) / (rj_target * t.rsub));
+  int rj = std::max(1, ((H + tiles - 1) / tiles + t.rsub - 1) / t.rsub);
   if (rows_override > 0) rj = std::max(1, rows_override / t.rsub);
   else
     while (rj > 4 && (int64_t)B * ((H + rj * t.rsub - 1) / (rj * t.rsub)) < 12ll * num_sms) rj /= 2;
