@@ -998,7 +998,34 @@ struct gclm_handle {
   size_t stage_bytes = 0;
   cudaStream_t hstream[2] = {nullptr, nullptr};
   cudaEvent_t hevent[2] = {nullptr, nullptr};
+  // opt-in timing of the pass launches (gclm_pass_timing): one event pair per solve, ring of TIMED
+  static constexpr int TIMED = 64;
+  bool timing = false;
+  cudaEvent_t tev[TIMED][2] = {};
+  int tpasses[TIMED] = {};
+  int64_t tcount = 0;
   char last_error[256] = {0};
+};
+
+// Event pair around the pass launches of one solve (only when timing is on; never while capturing).
+struct PassTimer {
+  gclm_handle* h; cudaStream_t s; int slot = -1;
+  PassTimer(gclm_handle* h_, cudaStream_t s_, int passes) : h(h_), s(s_) {
+    if (!h->timing) return;
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) return;
+    slot = (int)(h->tcount % gclm_handle::TIMED);
+    for (int k = 0; k < 2; k++)
+      if (!h->tev[slot][k] && cudaEventCreate(&h->tev[slot][k]) != cudaSuccess) { slot = -1; return; }
+    h->tpasses[slot] = passes;
+    cudaEventRecord(h->tev[slot][0], s);
+  }
+  void stop() {
+    if (slot < 0) return;
+    cudaEventRecord(h->tev[slot][1], s);
+    h->tcount++;
+    slot = -1;
+  }
 };
 
 // NCCL is bound at run time (dlopen) so that libgclm.so loads on boxes without NCCL / without a GPU.
@@ -1351,6 +1378,9 @@ int gclm_destroy(gclm_handle* h) {
     if (h->hstream[i]) cudaStreamDestroy(h->hstream[i]);
     if (h->hevent[i]) cudaEventDestroy(h->hevent[i]);
   }
+  for (int i = 0; i < gclm_handle::TIMED; i++)
+    for (int k = 0; k < 2; k++)
+      if (h->tev[i][k]) cudaEventDestroy(h->tev[i][k]);
   delete h;
   return GCLM_OK;
 }
@@ -1363,6 +1393,27 @@ int gclm_reserve(gclm_handle* h, int batch, int height, int width) {
 }
 
 int64_t gclm_launch_count(const gclm_handle* h) { return h ? h->launches : 0; }
+
+int gclm_pass_timing(gclm_handle* h, int enable) {
+  if (!h) return GCLM_ERR_INVALID_ARGUMENT;
+  h->timing = enable != 0;
+  h->tcount = 0;
+  return GCLM_OK;
+}
+
+int gclm_pass_time(gclm_handle* h, double* total_ms, int64_t* passes) {
+  if (!h || !total_ms || !passes) return GCLM_ERR_INVALID_ARGUMENT;
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  *total_ms = 0.0; *passes = 0;
+  const int64_t n = std::min<int64_t>(h->tcount, gclm_handle::TIMED);
+  for (int64_t i = 0; i < n; i++) {
+    float ms = 0.f;
+    CUDA_TRY(h, cudaEventSynchronize(h->tev[i][1]));
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->tev[i][0], h->tev[i][1]));
+    *total_ms += ms; *passes += h->tpasses[i];
+  }
+  return GCLM_OK;
+}
 
 int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt,
                const gclm_result* res, void* cuda_stream) {
@@ -1384,6 +1435,7 @@ int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt
   h->launches++;
   launch_sin_plane(h, prob, a, s);
   const dim3 grid((unsigned)((size_t)prob->batch * t.tiles_per_image)), block(t.nwarps * 32);
+  PassTimer timer(h, s, opt->num_steps + 1);
   for (int it = 0; it < opt->num_steps; it++) {
     a.pass = it; a.is_final = 0;
     launch_pass(a, !opt->use_log_focal, full, grid, block, s);
@@ -1392,6 +1444,7 @@ int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt
   a.pass = opt->num_steps; a.is_final = 1;
   launch_pass(a, true, full, grid, block, s);
   h->launches++;
+  timer.stop();
   CUDA_TRY(h, cudaGetLastError());
   return GCLM_OK;
 }
@@ -1425,6 +1478,7 @@ int gclm_solve_shared(gclm_handle* h, const gclm_problem* prob, const gclm_optio
   h->launches++;
   launch_sin_plane(h, prob, a, s);
   const dim3 grid((unsigned)((size_t)prob->batch * t.tiles_per_image)), block(t.nwarps * 32);
+  PassTimer timer(h, s, opt->num_steps + 1);  // here the bracket also holds the O(B) Schur kernels
   for (int it = 0; it < opt->num_steps; it++) {
     a.pass = it; a.is_final = 0;
     launch_pass(a, !opt->use_log_focal, full, grid, block, s);
@@ -1456,6 +1510,7 @@ int gclm_solve_shared(gclm_handle* h, const gclm_problem* prob, const gclm_optio
   a.pass = opt->num_steps; a.is_final = 1;
   launch_pass(a, true, full, grid, block, s);
   h->launches++;
+  timer.stop();
   CUDA_TRY(h, cudaGetLastError());
   return GCLM_OK;
 }

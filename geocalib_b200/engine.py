@@ -66,6 +66,16 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.gclm_launch_count(self._h))
 
+    def pass_timing(self, enable: bool) -> None:
+        """Start (and reset) / stop the opt-in event timing of the pass launches (bench.py's roofline)."""
+        _lib.check(self.lib.gclm_pass_timing(self._h, int(bool(enable))), "gclm_pass_timing")
+
+    def pass_time(self):
+        """(total ms, number of pass launches) of the solves enqueued since pass_timing(True); synchronises."""
+        ms, n = ctypes.c_double(0.0), ctypes.c_int64(0)
+        _lib.check(self.lib.gclm_pass_time(self._h, ctypes.byref(ms), ctypes.byref(n)), "gclm_pass_time")
+        return float(ms.value), int(n.value)
+
     def reserve(self, batch: int, height: int, width: int) -> None:
         _lib.check(self.lib.gclm_reserve(self._h, batch, height, width), "gclm_reserve")
 

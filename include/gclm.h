@@ -198,6 +198,17 @@ int gclm_solve_host(gclm_handle* h, const gclm_problem* prob, const gclm_options
 int64_t gclm_launch_count(const gclm_handle* h);
 
 /*
+ * Opt-in timing of the fused pass kernel (bench.py's roofline): while enabled, every gclm_solve /
+ * gclm_solve_shared records a CUDA event pair on the caller's stream around its num_steps + 1 pass
+ * launches (the once-per-solve set-up kernels stay outside the bracket).  gclm_pass_time waits for
+ * the solves enqueued since gclm_pass_timing(h, 1) (the last 64 at most) and returns the summed
+ * bracket time and the number of pass launches it covers.  Off by default; solves that are being
+ * captured into a CUDA graph are not timed.
+ */
+int gclm_pass_timing(gclm_handle* h, int enable);
+int gclm_pass_time(gclm_handle* h, double* total_ms, int64_t* passes);
+
+/*
  * Synthetic-field generator used by the benchmark: renders the perspective field of
  * the given cameras/gravities on device (get_perspective_field, perspective_fields.py:278-320),
  * adds N(0, sigma^2) noise, re-normalises the up vectors, draws confidences ~ U(conf_lo, 1).

@@ -672,3 +672,26 @@ def test_misaligned_planes(dev):
     torch.cuda.synchronize()
     assert torch.allclose(out["camera"]._data, ref["camera"]._data, rtol=1e-5)
     assert torch.allclose(out["gravity"]._data, ref["gravity"]._data, atol=1e-5)
+
+
+@pytest.mark.gpu
+def test_pass_timing_brackets_the_pass_launches(dev):
+    """gclm_pass_timing / gclm_pass_time: opt-in, counts num_steps + 1 launches per solve, no effect on results."""
+    import geocalib_b200 as G
+    from geocalib_b200.engine import get_engine
+    model, B, h, w = "pinhole", 4, 96, 128
+    cam, grav = synth_params(model, B, h, w, 5)
+    f = render_on_device(model, cam, grav, h, w, dev, sigma=0.02, seed=9)
+    opt = G.LMOptimizer({"camera_model": model, "num_steps": 7, "early_stop": False}).eval()
+    eng = get_engine(dev)
+    ref = opt(f)
+    assert eng.pass_time() == (0.0, 0)  # off by default
+    eng.pass_timing(True)
+    for _ in range(3):
+        out = opt(f)
+    ms, n = eng.pass_time()
+    eng.pass_timing(False)
+    assert n == 3 * 8 and 0.0 < ms < 1e3
+    assert torch.equal(out["camera"]._data, ref["camera"]._data)
+    opt(f)
+    assert eng.pass_time() == (0.0, 0)
