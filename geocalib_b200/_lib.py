@@ -80,6 +80,7 @@ SIGNATURES = {
     "gclm_comm_p2p_disable": (c_int, [c_void_p]),
     "gclm_solve_host": (c_int, [c_void_p, POINTER(Problem), POINTER(Options), POINTER(Result), c_int]),
     "gclm_launch_count": (c_int64, [c_void_p]),
+    "gclm_tile_config": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int32)]),
     "gclm_pass_timing": (c_int, [c_void_p, c_int]),
     "gclm_pass_time": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_int64)]),
     "gclm_render_fields": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_float,

@@ -1111,7 +1111,7 @@ TileCfg tile_config(int B, int H, int W, int num_sms, int rows_override, int max
   int rj = std::max(1, ((H + tiles - 1) / tiles + t.rsub - 1) / t.rsub);
   if (rows_override > 0) rj = std::max(1, rows_override / t.rsub);
   else
-    while (rj > 4 && (int64_t)B * ((H + rj * t.rsub - 1) / (rj * t.rsub)) < 12ll * num_sms) rj /= 2;
+    while (rj >= 8 && (int64_t)B * ((H + rj * t.rsub - 1) / (rj * t.rsub)) < 12ll * num_sms) rj /= 2;  // stays >= 4
   t.rows_per_tile = rj * t.rsub;
   t.tiles_per_image = (H + t.rows_per_tile - 1) / t.rows_per_tile;
   return t;
@@ -1393,6 +1393,17 @@ int gclm_reserve(gclm_handle* h, int batch, int height, int width) {
 }
 
 int64_t gclm_launch_count(const gclm_handle* h) { return h ? h->launches : 0; }
+
+int gclm_tile_config(int batch, int height, int width, int camera_model, int num_sms, int rows_per_tile,
+                     int32_t out[5]) {
+  if (!out || batch <= 0 || height <= 0 || width <= 0 || num_sms <= 0 || camera_model < 0 || camera_model > 3)
+    return GCLM_ERR_INVALID_ARGUMENT;
+  const TileCfg t = tile_config(batch, height, padded_width(width), num_sms, rows_per_tile,
+                                max_warps_for(camera_model, use_packed()));
+  out[0] = t.nwarps; out[1] = t.rsub; out[2] = t.rows_per_tile; out[3] = t.tiles_per_image;
+  out[4] = max_tiles_for(height, width);
+  return GCLM_OK;
+}
 
 int gclm_pass_timing(gclm_handle* h, int enable) {
   if (!h) return GCLM_ERR_INVALID_ARGUMENT;

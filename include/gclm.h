@@ -198,6 +198,14 @@ int gclm_solve_host(gclm_handle* h, const gclm_problem* prob, const gclm_options
 int64_t gclm_launch_count(const gclm_handle* h);
 
 /*
+ * How the pass kernel would tile a problem (host-only, no device needed): out = {warps per CTA,
+ * row bands per tile, rows per tile, tiles per image, tiles per image that gclm_reserve sizes for}.
+ * rows_per_tile as in gclm_options (0 = auto).  For tests and tuning.
+ */
+int gclm_tile_config(int batch, int height, int width, int camera_model, int num_sms, int rows_per_tile,
+                     int32_t out[5]);
+
+/*
  * Opt-in timing of the fused pass kernel (bench.py's roofline): while enabled, every gclm_solve /
  * gclm_solve_shared records a CUDA event pair on the caller's stream around its num_steps + 1 pass
  * launches (the once-per-solve set-up kernels stay outside the bracket).  gclm_pass_time waits for

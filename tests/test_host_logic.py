@@ -90,3 +90,27 @@ def test_gravity_container():
     J = g.J_rp()
     assert J.shape == (2, 3, 2)
     assert torch.allclose(torch.einsum("bij,bi->bj", J, g.vec3d), torch.zeros(2, 2), atol=1e-4)  # tangent
+
+
+def test_tile_config_balances_jobs_for_any_width():
+    """gclm_tile_config (host-only): every warp of the CTA gets the same number of (strip, band) jobs, the
+    tiles cover the image, and gclm_reserve sizes its partial-sum scratch for at least that many tiles."""
+    import ctypes
+    from geocalib_b200 import _lib
+    lib = _lib.load()
+    out = (ctypes.c_int32 * 5)()
+    for model in range(4):
+        for B in (1, 3, 64, 1024):
+            for H in (1, 5, 37, 240, 480, 1024, 2000):
+                for W in (4, 5, 36, 128, 320, 640, 768, 896, 1024, 1920, 4096):
+                    for rows in (0, 1, 32):
+                        assert lib.gclm_tile_config(B, H, W, model, 148, rows, out) == 0
+                        nwarps, rsub, rpt, tiles, reserved = list(out)
+                        ns = ((W + 3) // 4 * 4 + 127) // 128
+                        assert 1 <= nwarps <= 10 and rsub >= 1 and rpt >= 1
+                        assert (ns * rsub) % nwarps == 0, (model, B, H, W, rows, list(out))
+                        assert rpt % rsub == 0 and tiles == (H + rpt - 1) // rpt
+                        if rows == 0:
+                            assert tiles <= reserved, (model, B, H, W, list(out))
+    assert lib.gclm_tile_config(0, 480, 640, 0, 148, 0, out) < 0
+    assert lib.gclm_tile_config(1, 480, 640, 7, 148, 0, out) < 0
