@@ -201,9 +201,19 @@ __device__ __noinline__ void divisional_literal(float k1, float r2, ModelScalars
   m.om[0] = -r2 / mf(dn * dn);
 }
 
+// r2 == 0 ? if_zero : otherwise, per pixel
+__device__ __forceinline__ float select_zero(float r2, float if_zero, float otherwise) {
+  return r2 == 0.f ? if_zero : otherwise;
+}
+__device__ __forceinline__ f2 select_zero(f2 r2, float if_zero, f2 otherwise) {
+  return f2(r2.v.x == 0.f ? if_zero : otherwise.v.x, r2.v.y == 0.f ? if_zero : otherwise.v.y);
+}
+
 // LIT (simple_divisional, scalar only): evaluate the reference's literal masked formulas instead of
 // the closed form -- taken for pixels where the closed form does not apply (see divisional_is_cold).
-template <int MODEL, class V, bool LIT = false>
+// K0 (simple_divisional): k1 == 0 for the whole image (trivial init, or a zero distortion prior): the
+// literal formulas then reduce to the constants below, evaluated packed.
+template <int MODEL, class V, bool LIT = false, bool K0 = false>
 __device__ __forceinline__ void model_scalars(const PassConst& pc, V r2, ModelScalars<num_dist(MODEL), V>& m) {
   if constexpr (MODEL == PINHOLE) {  // camera.py:532-562 (never read: the K == 0 paths use constants)
     m.s = splat<V>(1.f); m.phi = m.A = m.Bc = m.Q = splat<V>(0.f); m.su = splat<V>(1.f);
@@ -231,6 +241,18 @@ __device__ __forceinline__ void model_scalars(const PassConst& pc, V r2, ModelSc
     //   s = 2/w, phi = A = 8 k1/(t w^2), Bc = 32 k1^2 (1+3t)/(t^3 w^3),
     //   ds/dk = 4 r^2/(t w^2), psi = 4 (1 + 2t - t^2)/(t^3 w^2).
     // The literal masked formulas (cold path) take over when k1 == 0 or the root is clamped.
+    if constexpr (K0) {
+      // divisional_literal at k1 == 0: every k1-proportional denominator is masked to 1e6 and its
+      // numerator is 0; what survives is A = 4/(2 r^2), Bc = -16/(4 r^4) - 4/r^4, psi = 16/4 - 2/1e6
+      // (and the masked values at the centre pixel, r^2 == 0)
+      const V ir = fast_rcp(r2);
+      m.s = splat<V>(1.f); m.phi = splat<V>(0.f);
+      m.A = select_zero(r2, 4.f / 1e6f, 2.f * ir);
+      m.Bc = select_zero(r2, -16.f / 1e6f - 4.f / 1e6f, -8.f * ir * ir);
+      m.sk[0] = splat<V>(0.f); m.psi[0] = splat<V>(16.f / 4.f - 2.f / 1e6f);
+      m.su = splat<V>(1.f); m.Q = splat<V>(0.f); m.om[0] = -r2;
+      return;
+    }
     if constexpr (LIT) {
       static_assert(!LIT || !is_f2<V>::value, "literal path is scalar");
       if constexpr (!is_f2<V>::value) divisional_literal(pc.k1, r2, m);
@@ -260,7 +282,7 @@ __device__ __forceinline__ void model_scalars(const PassConst& pc, V r2, ModelSc
 // ------------------------------------------------------------------------------------------
 struct FieldMask { bool up, lat, up_conf, lat_conf; };
 
-template <int MODEL, bool GEN_D, bool FULL, class V, bool LIT = false>
+template <int MODEL, bool GEN_D, bool FULL, class V, bool LIT = false, bool K0 = false>
 __device__ __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMask fm, V u,
                                                  float v, V ox, V oy, V sin_olat, V cu,
                                                  V cl, float inv_up2, float inv_lat2,
@@ -269,7 +291,7 @@ __device__ __forceinline__ void pixel_accumulate(const PassConst& pc, const Fiel
   const bool has_up = FULL || fm.up, has_lat = FULL || fm.lat;
   const V r2 = fmaf(u, u, splat<V>(v * v));
   ModelScalars<K, V> m;
-  model_scalars<MODEL, V, LIT>(pc, r2, m);
+  model_scalars<MODEL, V, LIT, K0>(pc, r2, m);
 
   V su_[NF], sl_[NF];  // Jacobian row scalars (up: along n_perp; latitude)
   V e = splat<V>(0.f), w_up = e, r_lat = e, w_lat = e;

@@ -644,9 +644,18 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
       const float v = ((float)y - pc.cy) * pc.inv_fy;
       // `ol` already holds target_lat = sin(latitude_field): sin_plane_kernel ran once before pass 0
       const float sl0 = ol.x, sl1 = ol.y, sl2 = ol.z, sl3 = ol.w;
+      if constexpr (MODEL == SIMPLE_DIVISIONAL && PACK) {
+        if (pc.k1 == 0.f) {  // whole image (first pass from the trivial init, zero prior): packed k1 == 0 form
+          pixel_accumulate<MODEL, GEN_D, FULL, f2, false, true>(pc, fm, f2(u[0], u[1]), v, f2(ox.x, ox.y), f2(oy.x, oy.y),
+                                                                f2(sl0, sl1), f2(cu.x, cu.y), f2(cl.x, cl.y), inv_up2, inv_lat2, acc);
+          pixel_accumulate<MODEL, GEN_D, FULL, f2, false, true>(pc, fm, f2(u[2], u[3]), v, f2(ox.z, ox.w), f2(oy.z, oy.w),
+                                                                f2(sl2, sl3), f2(cu.z, cu.w), f2(cl.z, cl.w), inv_up2, inv_lat2, acc);
+          return;
+        }
+      }
       if constexpr (MODEL == SIMPLE_DIVISIONAL) {
-        // rare pixels (all of them only while k1 == 0, i.e. the first pass from the trivial init) go
-        // through the literal masked formulas, one at a time
+        // rare pixels (clamped square root; with scalar math also the k1 == 0 passes) go through the
+        // literal masked formulas, one at a time
         const bool c0 = divisional_is_cold(pc, u[0], v), c1 = divisional_is_cold(pc, u[1], v);
         const bool c2 = divisional_is_cold(pc, u[2], v), c3 = divisional_is_cold(pc, u[3], v);
         if (c0 | c1 | c2 | c3) {
