@@ -18,6 +18,11 @@
 
 #include <type_traits>
 
+// The math below also compiles for the host (tests/host_math: the kernel's per-pixel code is checked
+// against the oracle without a GPU); hardware approximations and packed intrinsics then fall back to
+// plain C.
+#define GCLM_HD __host__ __device__
+
 namespace gclm {
 
 enum : int { PINHOLE = 0, SIMPLE_RADIAL = 1, RADIAL = 2, SIMPLE_DIVISIONAL = 3 };
@@ -38,15 +43,23 @@ constexpr int MAX_NACC = 15 + 5 + 2;
 // ------------------------------------------------------------------------------------------
 // fast hardware approximations used in the streaming pass only
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ float fast_rsqrt(float x) {
+GCLM_HD __forceinline__ float fast_rsqrt(float x) {
+#ifdef __CUDA_ARCH__
   float y;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#else
+  return 1.f / sqrtf(x);
+#endif
 }
-__device__ __forceinline__ float fast_rcp(float x) {
+GCLM_HD __forceinline__ float fast_rcp(float x) {
+#ifdef __CUDA_ARCH__
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+#else
+  return 1.f / x;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------
@@ -65,13 +78,13 @@ using ::fminf;
 
 struct f2 {
   float2 v;
-  __device__ __forceinline__ f2() {}
-  __device__ __forceinline__ explicit f2(float s) : v(make_float2(s, s)) {}
-  __device__ __forceinline__ f2(float a, float b) : v(make_float2(a, b)) {}
-  __device__ __forceinline__ explicit f2(float2 a) : v(a) {}
+  GCLM_HD __forceinline__ f2() {}
+  GCLM_HD __forceinline__ explicit f2(float s) : v(make_float2(s, s)) {}
+  GCLM_HD __forceinline__ f2(float a, float b) : v(make_float2(a, b)) {}
+  GCLM_HD __forceinline__ explicit f2(float2 a) : v(a) {}
 };
-__device__ __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
-__device__ __forceinline__ float2 bc2(f2 a) { return a.v; }
+GCLM_HD __forceinline__ float2 bc2(float s) { return make_float2(s, s); }
+GCLM_HD __forceinline__ float2 bc2(f2 a) { return a.v; }
 template <class T> struct is_f2 { static constexpr bool value = false; };
 template <> struct is_f2<f2> { static constexpr bool value = true; };
 #define GCLM_ANY_F2_2(A, B) typename = typename std::enable_if<is_f2<A>::value || is_f2<B>::value>::type
@@ -79,26 +92,52 @@ template <> struct is_f2<f2> { static constexpr bool value = true; };
   typename = typename std::enable_if<is_f2<A>::value || is_f2<B>::value || is_f2<C>::value>::type
 
 template <class A, class B, GCLM_ANY_F2_2(A, B)>
-__device__ __forceinline__ f2 operator*(A a, B b) { return f2(__fmul2_rn(bc2(a), bc2(b))); }
+GCLM_HD __forceinline__ f2 operator*(A a, B b) {
+#ifdef __CUDA_ARCH__
+  return f2(__fmul2_rn(bc2(a), bc2(b)));
+#else
+  const float2 x = bc2(a), y = bc2(b);
+  return f2(x.x * y.x, x.y * y.y);
+#endif
+}
 template <class A, class B, GCLM_ANY_F2_2(A, B)>
-__device__ __forceinline__ f2 operator+(A a, B b) { return f2(__fadd2_rn(bc2(a), bc2(b))); }
-__device__ __forceinline__ f2 operator-(f2 a) { return f2(-a.v.x, -a.v.y); }
+GCLM_HD __forceinline__ f2 operator+(A a, B b) {
+#ifdef __CUDA_ARCH__
+  return f2(__fadd2_rn(bc2(a), bc2(b)));
+#else
+  const float2 x = bc2(a), y = bc2(b);
+  return f2(x.x + y.x, x.y + y.y);
+#endif
+}
+GCLM_HD __forceinline__ f2 operator-(f2 a) { return f2(-a.v.x, -a.v.y); }
 template <class A, class B, GCLM_ANY_F2_2(A, B)>
-__device__ __forceinline__ f2 operator-(A a, B b) {
+GCLM_HD __forceinline__ f2 operator-(A a, B b) {
   const float2 nb = bc2(b);
+#ifdef __CUDA_ARCH__
   return f2(__fadd2_rn(bc2(a), make_float2(-nb.x, -nb.y)));
+#else
+  const float2 x = bc2(a);
+  return f2(x.x - nb.x, x.y - nb.y);
+#endif
 }
 template <class A, class B, class C, GCLM_ANY_F2_3(A, B, C)>
-__device__ __forceinline__ f2 fmaf(A a, B b, C c) { return f2(__ffma2_rn(bc2(a), bc2(b), bc2(c))); }
-__device__ __forceinline__ f2 fmaxf(f2 a, float s) { return f2(::fmaxf(a.v.x, s), ::fmaxf(a.v.y, s)); }
-__device__ __forceinline__ f2 fminf(f2 a, float s) { return f2(::fminf(a.v.x, s), ::fminf(a.v.y, s)); }
-__device__ __forceinline__ f2 fast_rsqrt(f2 a) { return f2(fast_rsqrt(a.v.x), fast_rsqrt(a.v.y)); }
-__device__ __forceinline__ f2 fast_rcp(f2 a) { return f2(fast_rcp(a.v.x), fast_rcp(a.v.y)); }
-__device__ __forceinline__ float hsum(float a) { return a; }
-__device__ __forceinline__ float hsum(f2 a) { return a.v.x + a.v.y; }
-template <class V> __device__ __forceinline__ V splat(float s);
-template <> __device__ __forceinline__ float splat<float>(float s) { return s; }
-template <> __device__ __forceinline__ f2 splat<f2>(float s) { return f2(s); }
+GCLM_HD __forceinline__ f2 fmaf(A a, B b, C c) {
+#ifdef __CUDA_ARCH__
+  return f2(__ffma2_rn(bc2(a), bc2(b), bc2(c)));
+#else
+  const float2 x = bc2(a), y = bc2(b), z = bc2(c);
+  return f2(::fmaf(x.x, y.x, z.x), ::fmaf(x.y, y.y, z.y));
+#endif
+}
+GCLM_HD __forceinline__ f2 fmaxf(f2 a, float s) { return f2(::fmaxf(a.v.x, s), ::fmaxf(a.v.y, s)); }
+GCLM_HD __forceinline__ f2 fminf(f2 a, float s) { return f2(::fminf(a.v.x, s), ::fminf(a.v.y, s)); }
+GCLM_HD __forceinline__ f2 fast_rsqrt(f2 a) { return f2(fast_rsqrt(a.v.x), fast_rsqrt(a.v.y)); }
+GCLM_HD __forceinline__ f2 fast_rcp(f2 a) { return f2(fast_rcp(a.v.x), fast_rcp(a.v.y)); }
+GCLM_HD __forceinline__ float hsum(float a) { return a; }
+GCLM_HD __forceinline__ float hsum(f2 a) { return a.v.x + a.v.y; }
+template <class V> GCLM_HD __forceinline__ V splat(float s);
+template <> GCLM_HD __forceinline__ float splat<float>(float s) { return s; }
+template <> GCLM_HD __forceinline__ f2 splat<f2>(float s) { return f2(s); }
 
 // ------------------------------------------------------------------------------------------
 // per-image constants of one pass (hoisted out of the pixel loop)
@@ -112,7 +151,7 @@ struct PassConst {
 };
 
 // ---- gravity helpers: geocalib/misc.py:181-259, geocalib/gravity.py:62-101 ----
-__device__ inline void householder(const float g[3], float hv[3], float& beta) {
+GCLM_HD inline void householder(const float g[3], float hv[3], float& beta) {
   float sigma = g[0] * g[0] + g[1] * g[1];
   const float xpiv = g[2];
   const float nrm = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
@@ -122,7 +161,7 @@ __device__ inline void householder(const float g[3], float hv[3], float& beta) {
   hv[0] = g[0] / vpiv; hv[1] = g[1] / vpiv; hv[2] = 1.f;
 }
 
-__device__ inline void gravity_rp(const float g[3], float& roll, float& pitch) {
+GCLM_HD inline void gravity_rp(const float g[3], float& roll, float& pitch) {
   // gravity.py:15,62-67: note the 1e-4 eps in the roll read-back
   const float r = asinf(-g[0] / (sqrtf(1.f - g[2] * g[2]) + 1e-4f));
   const float sgn = g[0] > 0.f ? 1.f : (g[0] < 0.f ? -1.f : 0.f);
@@ -130,14 +169,14 @@ __device__ inline void gravity_rp(const float g[3], float& roll, float& pitch) {
   pitch = asinf(g[2]);
 }
 
-__device__ inline void normalize3(float g[3]) {  // F.normalize, eps 1e-12 (gravity.py:26)
+GCLM_HD inline void normalize3(float g[3]) {  // F.normalize, eps 1e-12 (gravity.py:26)
   const float n = fmaxf(sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]), 1e-12f);
   g[0] /= n; g[1] /= n; g[2] /= n;
 }
 
 // cam = [w h fx fy cx cy k1 k2], g unit.  rpf: use the (roll,pitch) basis and the non-log focal
 // direction (estimate_uncertainty -> setup_system(as_rpf=True), lm_optimizer.py:411-416,481-483).
-__device__ inline void make_pass_const(const float* cam, const float* g, bool spherical,
+GCLM_HD inline void make_pass_const(const float* cam, const float* g, bool spherical,
                                        bool log_focal, bool rpf, PassConst& pc) {
   pc.inv_fx = 1.f / cam[2]; pc.inv_fy = 1.f / cam[3];
   pc.cx = cam[4]; pc.cy = cam[5]; pc.k1 = cam[6]; pc.k2 = cam[7];
@@ -176,7 +215,7 @@ struct ModelScalars {
 // Used only when the cancellation-free closed form does not apply: k1 == 0 (trivial init, the
 // masked branches make ds/dk = 0 and J_o = 2/r^2 I - 8/r^4 uv uv^T) or
 // 1 - 4 k1 r^2 < 1e-6 (clamped square root).  Cold path.
-__device__ __noinline__ void divisional_literal(float k1, float r2, ModelScalars<1, float>& m) {
+GCLM_HD __noinline__ void divisional_literal(float k1, float r2, ModelScalars<1, float>& m) {
   auto mf = [](float d) { return d == 0.f ? 1e6f : d; };
   const float x = 1.f - 4.f * k1 * r2;
   const float rad = 1.f - sqrtf(fmaxf(x, 0.f));
@@ -202,10 +241,10 @@ __device__ __noinline__ void divisional_literal(float k1, float r2, ModelScalars
 }
 
 // r2 == 0 ? if_zero : otherwise, per pixel
-__device__ __forceinline__ float select_zero(float r2, float if_zero, float otherwise) {
+GCLM_HD __forceinline__ float select_zero(float r2, float if_zero, float otherwise) {
   return r2 == 0.f ? if_zero : otherwise;
 }
-__device__ __forceinline__ f2 select_zero(f2 r2, float if_zero, f2 otherwise) {
+GCLM_HD __forceinline__ f2 select_zero(f2 r2, float if_zero, f2 otherwise) {
   return f2(r2.v.x == 0.f ? if_zero : otherwise.v.x, r2.v.y == 0.f ? if_zero : otherwise.v.y);
 }
 
@@ -214,7 +253,7 @@ __device__ __forceinline__ f2 select_zero(f2 r2, float if_zero, f2 otherwise) {
 // K0 (simple_divisional): k1 == 0 for the whole image (trivial init, or a zero distortion prior): the
 // literal formulas then reduce to the constants below, evaluated packed.
 template <int MODEL, class V, bool LIT = false, bool K0 = false>
-__device__ __forceinline__ void model_scalars(const PassConst& pc, V r2, ModelScalars<num_dist(MODEL), V>& m) {
+GCLM_HD __forceinline__ void model_scalars(const PassConst& pc, V r2, ModelScalars<num_dist(MODEL), V>& m) {
   if constexpr (MODEL == PINHOLE) {  // camera.py:532-562 (never read: the K == 0 paths use constants)
     m.s = splat<V>(1.f); m.phi = m.A = m.Bc = m.Q = splat<V>(0.f); m.su = splat<V>(1.f);
   } else if constexpr (MODEL == SIMPLE_RADIAL) {  // camera.py:611-660
@@ -283,7 +322,7 @@ __device__ __forceinline__ void model_scalars(const PassConst& pc, V r2, ModelSc
 struct FieldMask { bool up, lat, up_conf, lat_conf; };
 
 template <int MODEL, bool GEN_D, bool FULL, class V, bool LIT = false, bool K0 = false>
-__device__ __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMask fm, V u,
+GCLM_HD __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMask fm, V u,
                                                  float v, V ox, V oy, V sin_olat, V cu,
                                                  V cl, float inv_up2, float inv_lat2,
                                                  V (&acc)[Dims<MODEL>::NACC]) {
@@ -432,14 +471,14 @@ __device__ __forceinline__ void pixel_accumulate(const PassConst& pc, const Fiel
 
 // simple_divisional: does pixel (u, v) need the literal masked formulas?  k1 == 0 (trivial init:
 // every masked branch fires) or 1 - 4 k1 r^2 < 1e-6 (clamped square root).
-__device__ __forceinline__ bool divisional_is_cold(const PassConst& pc, float u, float v) {
+GCLM_HD __forceinline__ bool divisional_is_cold(const PassConst& pc, float u, float v) {
   return pc.k1 == 0.f || fmaf(-4.f * pc.k1, fmaf(u, u, v * v), 1.f) < 1e-6f;
 }
 // Cold path: one pixel through the scalar code with the literal formulas; returns its contribution
 // in d[NACC] (local memory is fine here) so that the hot loop's packed accumulators never have
 // their address taken.
 template <int MODEL, bool GEN_D, bool FULL, bool LIT>
-__device__ __noinline__ void pixel_scalar(const PassConst& pc, const FieldMask fm, float u, float v, float ox,
+GCLM_HD __noinline__ void pixel_scalar(const PassConst& pc, const FieldMask fm, float u, float v, float ox,
                                            float oy, float sin_olat, float cu, float cl, float inv_up2,
                                            float inv_lat2, float* d) {
   float a1[Dims<MODEL>::NACC];
@@ -450,12 +489,70 @@ __device__ __noinline__ void pixel_scalar(const PassConst& pc, const FieldMask f
   for (int i = 0; i < Dims<MODEL>::NACC; i++) d[i] = a1[i];
 }
 
+// Normalised image coordinates of pixel column x / row y (integer pixel centres, camera.py:335-338).
+GCLM_HD __forceinline__ float pixel_u(const PassConst& pc, int x) { return ((float)x - pc.cx) * pc.inv_fx; }
+GCLM_HD __forceinline__ float pixel_v(const PassConst& pc, int y) { return ((float)y - pc.cy) * pc.inv_fy; }
+
+// Four consecutive pixels of one image row (one float4 of every plane; `ol` = sin(latitude)) into the
+// accumulators: the body of lm_pass_kernel's streaming loop, also run on the host by tests/host_math.
+template <int MODEL, bool GEN_D, bool FULL, bool PACK>
+GCLM_HD __forceinline__ void row_accumulate(const PassConst& pc, const FieldMask fm, const float (&u)[4], float v,
+                                            const float4 ox, const float4 oy, const float4 ol, const float4 cu,
+                                            const float4 cl, float inv_up2, float inv_lat2,
+                                            typename std::conditional<PACK, f2, float>::type (&acc)[Dims<MODEL>::NACC]) {
+  constexpr int NACC = Dims<MODEL>::NACC;
+  using V = typename std::conditional<PACK, f2, float>::type;
+  const float sl0 = ol.x, sl1 = ol.y, sl2 = ol.z, sl3 = ol.w;
+  if constexpr (MODEL == SIMPLE_DIVISIONAL && PACK) {
+    if (pc.k1 == 0.f) {  // whole image (first pass from the trivial init, zero prior): packed k1 == 0 form
+      pixel_accumulate<MODEL, GEN_D, FULL, f2, false, true>(pc, fm, f2(u[0], u[1]), v, f2(ox.x, ox.y), f2(oy.x, oy.y),
+                                                            f2(sl0, sl1), f2(cu.x, cu.y), f2(cl.x, cl.y), inv_up2, inv_lat2, acc);
+      pixel_accumulate<MODEL, GEN_D, FULL, f2, false, true>(pc, fm, f2(u[2], u[3]), v, f2(ox.z, ox.w), f2(oy.z, oy.w),
+                                                            f2(sl2, sl3), f2(cu.z, cu.w), f2(cl.z, cl.w), inv_up2, inv_lat2, acc);
+      return;
+    }
+  }
+  if constexpr (MODEL == SIMPLE_DIVISIONAL) {
+    // rare pixels (clamped square root; with scalar math also the k1 == 0 passes) go through the
+    // literal masked formulas, one at a time
+    const bool c0 = divisional_is_cold(pc, u[0], v), c1 = divisional_is_cold(pc, u[1], v);
+    const bool c2 = divisional_is_cold(pc, u[2], v), c3 = divisional_is_cold(pc, u[3], v);
+    if (c0 | c1 | c2 | c3) {
+      float d[NACC];
+      const float us[4] = {u[0], u[1], u[2], u[3]};
+      const float oxs[4] = {ox.x, ox.y, ox.z, ox.w}, oys[4] = {oy.x, oy.y, oy.z, oy.w};
+      const float sls[4] = {sl0, sl1, sl2, sl3}, cus[4] = {cu.x, cu.y, cu.z, cu.w}, cls[4] = {cl.x, cl.y, cl.z, cl.w};
+      const bool cold[4] = {c0, c1, c2, c3};
+      constexpr float share = is_f2<V>::value ? 0.5f : 1.f;  // packed: both halves of an accumulator sum to d
+#pragma unroll 1
+      for (int i = 0; i < 4; i++) {
+        if (cold[i]) pixel_scalar<MODEL, GEN_D, FULL, true>(pc, fm, us[i], v, oxs[i], oys[i], sls[i], cus[i], cls[i], inv_up2, inv_lat2, d);
+        else pixel_scalar<MODEL, GEN_D, FULL, false>(pc, fm, us[i], v, oxs[i], oys[i], sls[i], cus[i], cls[i], inv_up2, inv_lat2, d);
+#pragma unroll
+        for (int k = 0; k < NACC; k++) acc[k] = acc[k] + splat<V>(share * d[k]);
+      }
+      return;
+    }
+  }
+  if constexpr (PACK) {
+    pixel_accumulate<MODEL, GEN_D, FULL, f2>(pc, fm, f2(u[0], u[1]), v, f2(ox.x, ox.y), f2(oy.x, oy.y),
+                                             f2(sl0, sl1), f2(cu.x, cu.y), f2(cl.x, cl.y), inv_up2, inv_lat2, acc);
+    pixel_accumulate<MODEL, GEN_D, FULL, f2>(pc, fm, f2(u[2], u[3]), v, f2(ox.z, ox.w), f2(oy.z, oy.w),
+                                             f2(sl2, sl3), f2(cu.z, cu.w), f2(cl.z, cl.w), inv_up2, inv_lat2, acc);
+  } else {
+    pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[0], v, ox.x, oy.x, sl0, cu.x, cl.x, inv_up2, inv_lat2, acc);
+    pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[1], v, ox.y, oy.y, sl1, cu.y, cl.y, inv_up2, inv_lat2, acc);
+    pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[2], v, ox.z, oy.z, sl2, cu.z, cl.z, inv_up2, inv_lat2, acc);
+    pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[3], v, ox.w, oy.w, sl3, cu.w, cl.w, inv_up2, inv_lat2, acc);
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // small dense linear algebra (n <= 5), single thread
 // ------------------------------------------------------------------------------------------
 // In-place lower Cholesky; returns false when not positive definite (torch.linalg.cholesky raises,
 // lm_optimizer.py:129-133).
-__device__ inline bool cholesky(float* A, int n) {
+GCLM_HD inline bool cholesky(float* A, int n) {
   for (int j = 0; j < n; j++) {
     float d = A[j * n + j];
     for (int k = 0; k < j; k++) d -= A[j * n + k] * A[j * n + k];
@@ -470,7 +567,7 @@ __device__ inline bool cholesky(float* A, int n) {
   }
   return true;
 }
-__device__ inline void cholesky_solve(const float* L, int n, float* b) {
+GCLM_HD inline void cholesky_solve(const float* L, int n, float* b) {
   for (int i = 0; i < n; i++) {
     float s = b[i];
     for (int k = 0; k < i; k++) s -= L[i * n + k] * b[k];
@@ -483,7 +580,7 @@ __device__ inline void cholesky_solve(const float* L, int n, float* b) {
   }
 }
 // Gauss-Jordan inverse with partial pivoting (torch.inverse, lm_optimizer.py:484).
-__device__ inline bool invert(const float* A, int n, float* Ainv) {
+GCLM_HD inline bool invert(const float* A, int n, float* Ainv) {
   float a[MAX_NF][2 * MAX_NF];
   for (int i = 0; i < n; i++)
     for (int j = 0; j < n; j++) { a[i][j] = A[i * n + j]; a[i][n + j] = i == j ? 1.f : 0.f; }
@@ -506,7 +603,7 @@ __device__ inline bool invert(const float* A, int n, float* Ainv) {
 // ------------------------------------------------------------------------------------------
 // parameter updates: lm_optimizer.py:518-549
 // ------------------------------------------------------------------------------------------
-__device__ inline void gravity_update(float g[3], float d0, float d1, bool spherical) {
+GCLM_HD inline void gravity_update(float g[3], float d0, float d1, bool spherical) {
   if (spherical) {  // SphericalManifold.plus, misc.py:233-259
     const float nx = sqrtf(g[0] * g[0] + g[1] * g[1] + g[2] * g[2]);
     const float nd = sqrtf(d0 * d0 + d1 * d1);
@@ -529,7 +626,7 @@ __device__ inline void gravity_update(float g[3], float d0, float d1, bool spher
   normalize3(g);
 }
 
-__device__ inline void focal_update(float cam[8], float delta, bool as_log) {  // camera.py:136-152
+GCLM_HD inline void focal_update(float cam[8], float delta, bool as_log) {  // camera.py:136-152
   const float h = cam[1];
   float fy = as_log ? expf(logf(cam[3]) + delta) : cam[3] + delta;
   const float pi = 3.14159265358979323846f;
@@ -540,7 +637,7 @@ __device__ inline void focal_update(float cam[8], float delta, bool as_log) {  /
   cam[2] = fx; cam[3] = fy;
 }
 
-__device__ inline void dist_update(int model, float cam[8], const float* d) {
+GCLM_HD inline void dist_update(int model, float cam[8], const float* d) {
   // camera.py:599-604,700-705,817-822.  `dist` is _data[6:] (2 wide) for one-parameter models, so
   // delta k1 is broadcast into the unused k2 slot as well -- kept for bit-level
   // equality of camera._data.

@@ -629,7 +629,7 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
 #endif
     float u[4];
 #pragma unroll
-    for (int i = 0; i < 4; i++) u[i] = ((float)(x0 + i) - pc.cx) * pc.inv_fx;
+    for (int i = 0; i < 4; i++) u[i] = pixel_u(pc, x0 + i);
     const size_t off = (size_t)y0 * W + x0;
     const float* p_ux = (FULL || fm.up) ? a.up + (size_t)b * 2 * N + off : nullptr;
     const float* p_lat = (FULL || fm.lat) ? a.lat + (size_t)b * N + off : nullptr;
@@ -641,50 +641,8 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
                                  cu.x + cu.y + cu.z + cu.w + cl.x + cl.y + cl.z + cl.w + (float)y);
       return;
 #endif
-      const float v = ((float)y - pc.cy) * pc.inv_fy;
       // `ol` already holds target_lat = sin(latitude_field): sin_plane_kernel ran once before pass 0
-      const float sl0 = ol.x, sl1 = ol.y, sl2 = ol.z, sl3 = ol.w;
-      if constexpr (MODEL == SIMPLE_DIVISIONAL && PACK) {
-        if (pc.k1 == 0.f) {  // whole image (first pass from the trivial init, zero prior): packed k1 == 0 form
-          pixel_accumulate<MODEL, GEN_D, FULL, f2, false, true>(pc, fm, f2(u[0], u[1]), v, f2(ox.x, ox.y), f2(oy.x, oy.y),
-                                                                f2(sl0, sl1), f2(cu.x, cu.y), f2(cl.x, cl.y), inv_up2, inv_lat2, acc);
-          pixel_accumulate<MODEL, GEN_D, FULL, f2, false, true>(pc, fm, f2(u[2], u[3]), v, f2(ox.z, ox.w), f2(oy.z, oy.w),
-                                                                f2(sl2, sl3), f2(cu.z, cu.w), f2(cl.z, cl.w), inv_up2, inv_lat2, acc);
-          return;
-        }
-      }
-      if constexpr (MODEL == SIMPLE_DIVISIONAL) {
-        // rare pixels (clamped square root; with scalar math also the k1 == 0 passes) go through the
-        // literal masked formulas, one at a time
-        const bool c0 = divisional_is_cold(pc, u[0], v), c1 = divisional_is_cold(pc, u[1], v);
-        const bool c2 = divisional_is_cold(pc, u[2], v), c3 = divisional_is_cold(pc, u[3], v);
-        if (c0 | c1 | c2 | c3) {
-          float d[NACC];
-          const float us[4] = {u[0], u[1], u[2], u[3]};
-          const float oxs[4] = {ox.x, ox.y, ox.z, ox.w}, oys[4] = {oy.x, oy.y, oy.z, oy.w};
-          const float sls[4] = {sl0, sl1, sl2, sl3}, cus[4] = {cu.x, cu.y, cu.z, cu.w}, cls[4] = {cl.x, cl.y, cl.z, cl.w};
-          const bool cold[4] = {c0, c1, c2, c3};
-#pragma unroll 1
-          for (int i = 0; i < 4; i++) {
-            if (cold[i]) pixel_scalar<MODEL, GEN_D, FULL, true>(pc, fm, us[i], v, oxs[i], oys[i], sls[i], cus[i], cls[i], inv_up2, inv_lat2, d);
-            else pixel_scalar<MODEL, GEN_D, FULL, false>(pc, fm, us[i], v, oxs[i], oys[i], sls[i], cus[i], cls[i], inv_up2, inv_lat2, d);
-#pragma unroll
-            for (int k = 0; k < NACC; k++) acc[k] = acc[k] + splat<V>(0.5f * d[k]);  // both halves sum to d
-          }
-          return;
-        }
-      }
-      if constexpr (PACK) {
-        pixel_accumulate<MODEL, GEN_D, FULL, f2>(pc, fm, f2(u[0], u[1]), v, f2(ox.x, ox.y), f2(oy.x, oy.y),
-                                                 f2(sl0, sl1), f2(cu.x, cu.y), f2(cl.x, cl.y), inv_up2, inv_lat2, acc);
-        pixel_accumulate<MODEL, GEN_D, FULL, f2>(pc, fm, f2(u[2], u[3]), v, f2(ox.z, ox.w), f2(oy.z, oy.w),
-                                                 f2(sl2, sl3), f2(cu.z, cu.w), f2(cl.z, cl.w), inv_up2, inv_lat2, acc);
-      } else {
-        pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[0], v, ox.x, oy.x, sl0, cu.x, cl.x, inv_up2, inv_lat2, acc);
-        pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[1], v, ox.y, oy.y, sl1, cu.y, cl.y, inv_up2, inv_lat2, acc);
-        pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[2], v, ox.z, oy.z, sl2, cu.z, cl.z, inv_up2, inv_lat2, acc);
-        pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[3], v, ox.w, oy.w, sl3, cu.w, cl.w, inv_up2, inv_lat2, acc);
-      }
+      row_accumulate<MODEL, GEN_D, FULL, PACK>(pc, fm, u, pixel_v(pc, y), ox, oy, ol, cu, cl, inv_up2, inv_lat2, acc);
     };
 #ifdef GCLM_TMA2D
     if constexpr (FULL) {

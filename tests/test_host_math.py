@@ -1,0 +1,137 @@
+"""The CUDA source's per-pixel math, compiled for the HOST, against the oracle -- no GPU needed.
+
+tests/host_math/host_math.cu includes geocalib_b200/csrc/gclm_device.cuh and drives the same
+`row_accumulate` the pass kernel's streaming loop calls (packed and scalar builds, log-focal and general focal
+direction, the divisional k1 == 0 / clamped-root special cases).  Its sums over the pixels are compared with
+the fp64 oracle system (G, H, costs) at an estimate that is NOT the one the fields were rendered from, so that
+residuals, Huber weights (inliers and outliers) and every Jacobian column matter.
+"""
+import ctypes
+import shutil
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+from oracle import oracle
+
+HERE = Path(__file__).resolve().parent / "host_math"
+MODELS = ["pinhole", "simple_radial", "radial", "simple_divisional"]
+NUM_DIST = {"pinhole": 0, "simple_radial": 1, "radial": 2, "simple_divisional": 1}
+
+
+@pytest.fixture(scope="module")
+def hostmath():
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not Path(nvcc).exists():
+        pytest.skip("nvcc not available")
+    src, lib = HERE / "host_math.cu", HERE / "libgclm_hostmath.so"
+    hdr = HERE.parents[1] / "geocalib_b200" / "csrc" / "gclm_device.cuh"
+    if not lib.exists() or lib.stat().st_mtime < max(src.stat().st_mtime, hdr.stat().st_mtime):
+        subprocess.run([nvcc, "-O2", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC",
+                        "-Xcompiler", "-Wno-unknown-pragmas", "-shared", "-o", str(lib), str(src)], check=True)
+    L = ctypes.CDLL(str(lib))
+    fp, dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
+    L.gclm_host_math_system.restype = ctypes.c_int
+    L.gclm_host_math_system.argtypes = [ctypes.c_int] * 3 + [fp] * 6 + [ctypes.c_int] * 5 + [ctypes.c_float] * 2 + [dp]
+    return L
+
+
+def gt_and_estimate(model, h, w, seed, k1=None):
+    rng = np.random.default_rng(seed)
+    fish = model == "simple_divisional"
+    def cam_of(vfov_deg, k1v, k2v):
+        fy = h / 2 / np.tan(np.deg2rad(vfov_deg) / 2)
+        return np.array([w, h, fy * 1.05, fy, w / 2, h / 2, k1v, k2v], np.float32)
+    k1_gt = {"pinhole": 0.0, "simple_radial": 0.08, "radial": -0.1, "simple_divisional": -0.2}[model]
+    k2_gt = 0.02 if model == "radial" else 0.0
+    cam_gt = cam_of(95 if fish else 60, k1_gt, k2_gt)
+    grav_gt = oracle.gravity_from_rp(0.3, -0.25).astype(np.float32)
+    # the estimate the system is evaluated at: a few degrees / 15 % away from the truth
+    k1_est = k1_gt * 0.5 if k1 is None else k1
+    cam = cam_of(105 if fish else 70, k1_est, 0.5 * k2_gt)
+    grav = oracle.gravity_from_rp(0.22, -0.15).astype(np.float32)
+    up, lat = oracle.render(model, cam_gt, grav_gt, h, w)
+    up = up + rng.normal(0, 0.02, up.shape).astype(np.float32)
+    up /= np.linalg.norm(up, axis=0, keepdims=True)
+    lat = lat + rng.normal(0, 0.02, lat.shape).astype(np.float32)
+    # a block of gross outliers: Huber's linear branch
+    up[:, : h // 4, : w // 4] = np.array([0.6, -0.8], np.float32)[:, None, None]
+    lat[:, : h // 4, w // 2:] += 0.5
+    uconf = rng.uniform(0.2, 1.0, (h, w)).astype(np.float32)
+    lconf = rng.uniform(0.2, 1.0, (h, w)).astype(np.float32)
+    return cam, grav, np.ascontiguousarray(up, np.float32), np.ascontiguousarray(lat, np.float32), uconf, lconf
+
+
+def host_system(L, model, cam, grav, up, lat, uconf, lconf, *, spherical, log_focal, rpf, pack, force_gen_d=False):
+    h, w = lat.shape[-2:]
+    nf = 3 + NUM_DIST[model]
+    nh = nf * (nf + 1) // 2
+    out = np.zeros(nh + nf + 2, np.float64)
+    fp = lambda a: np.ascontiguousarray(a, np.float32).ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    n = L.gclm_host_math_system(MODELS.index(model), h, w, fp(up), fp(lat), fp(uconf), fp(lconf), fp(cam), fp(grav),
+                                int(spherical), int(log_focal), int(rpf), int(pack), int(force_gen_d), 1e-2, 1e-2,
+                                out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+    assert n == out.size
+    H = np.zeros((nf, nf))
+    H[np.triu_indices(nf)] = out[:nh]
+    H = H + np.triu(H, 1).T
+    costs = out[nh + nf:] * 1e-4 / (h * w)  # the epilogue's scale^2 / N
+    return out[nh:nh + nf], H, costs
+
+
+def assert_system_close(got, ref, tol=3e-6):
+    """fp32 pixel math vs the fp64 oracle: measured differences are ~1e-7 in the scale of the system."""
+    G, H, c = got
+    Gr, Hr, cr = (np.asarray(a, np.float64) for a in ref)
+    # compare in the scale of the system (sqrt of the diagonal), as the GPU parity test does
+    d = np.sqrt(np.maximum(np.diag(Hr), 1e-30))
+    assert np.abs((H - Hr) / np.outer(d, d)).max() < tol, np.abs((H - Hr) / np.outer(d, d)).max()
+    assert np.abs((G - Gr) / d).max() < tol * np.abs(Gr / d).max() + 1e-6, np.abs((G - Gr) / d).max()
+    assert np.allclose(c, cr, rtol=2e-6, atol=1e-12), (c, cr)
+
+
+@pytest.mark.parametrize("pack", [1, 0], ids=["packed", "scalar"])
+@pytest.mark.parametrize("basis", ["lm_pass", "linear_focal_euclidean", "rpf_final"])
+@pytest.mark.parametrize("model", MODELS)
+def test_kernel_math_matches_oracle(hostmath, model, basis, pack):
+    h, w = 48, 64
+    cam, grav, up, lat, uconf, lconf = gt_and_estimate(model, h, w, 3)
+    kw = {"lm_pass": dict(spherical=True, log_focal=True, rpf=False),
+          "linear_focal_euclidean": dict(spherical=False, log_focal=False, rpf=False),
+          "rpf_final": dict(spherical=True, log_focal=True, rpf=True)}[basis]
+    got = host_system(hostmath, model, cam, grav, up, lat, uconf, lconf, pack=pack, **kw)
+    ref = oracle.system(model, cam, grav, up, lat[None], uconf, lconf, rpf_basis=kw["rpf"], spherical=kw["spherical"],
+                        log_focal=kw["log_focal"], dtype=np.float64)
+    assert_system_close(got, ref)
+    if basis == "lm_pass":  # the general-focal-direction code must agree with the log-focal specialisation
+        gen = host_system(hostmath, model, cam, grav, up, lat, uconf, lconf, pack=pack, force_gen_d=True, **kw)
+        assert_system_close(gen, ref)
+
+
+@pytest.mark.parametrize("pack", [1, 0], ids=["packed", "scalar"])
+@pytest.mark.parametrize("rpf", [False, True], ids=["lm_pass", "rpf_final"])
+def test_divisional_k1_zero_masked_branches(hostmath, pack, rpf):
+    """k1 == 0 (trivial init / zero prior): the reference's masked denominators; the packed build
+    uses the constant form (model_scalars<..., K0>), the scalar build the literal formulas; centre pixel r^2 = 0."""
+    h, w = 48, 64  # even: pixel (w/2, h/2) has u = v = 0
+    cam, grav, up, lat, uconf, lconf = gt_and_estimate("simple_divisional", h, w, 5, k1=0.0)
+    got = host_system(hostmath, "simple_divisional", cam, grav, up, lat, uconf, lconf, spherical=True, log_focal=True,
+                      rpf=rpf, pack=pack)
+    ref = oracle.system("simple_divisional", cam, grav, up, lat[None], uconf, lconf, rpf_basis=rpf, dtype=np.float64)
+    assert_system_close(got, ref)
+
+
+@pytest.mark.parametrize("pack", [1, 0], ids=["packed", "scalar"])
+def test_divisional_clamped_root_pixels(hostmath, pack):
+    """k1 > 0 large enough that 1 - 4 k1 r^2 < 1e-6 in the image corners: those pixels take the literal path."""
+    h, w = 48, 64
+    cam, grav, up, lat, uconf, lconf = gt_and_estimate("simple_divisional", h, w, 7, k1=0.45)
+    fy = cam[3]
+    r2_corner = (w / 2 / cam[2]) ** 2 + (h / 2 / fy) ** 2
+    assert 1 - 4 * 0.45 * r2_corner < 0, "the test image must contain clamped pixels"
+    got = host_system(hostmath, "simple_divisional", cam, grav, up, lat, uconf, lconf, spherical=True, log_focal=True,
+                      rpf=False, pack=pack)
+    ref = oracle.system("simple_divisional", cam, grav, up, lat[None], uconf, lconf, dtype=np.float64)
+    assert_system_close(got, ref, tol=2e-4)  # Jacobians blow up next to the clamp (condition number ~1e10)
