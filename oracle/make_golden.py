@@ -14,6 +14,12 @@ own functions:
                        (fp32 and fp64; optimisation basis and as_rpf basis)
   lm_<case>.npz        LMOptimizer(conf).eval().forward(data) end to end
   init.npz             get_trivial_estimation for a few shapes / priors / scales
+  base_<case>.npz      BASELINE.json configs at their real image sizes (640x480, 1024x1024, and the
+                       single 320x240 image of config 0): the inputs are NOT stored (6-12 MB each) but
+                       regenerated from a seeded recipe (oracle.procedural_fields, checksummed);
+                       stored are the reference's outputs, its iteration-0 system (G, H, costs in
+                       fp64 at the trivial initial estimate) and 1/2/3-iteration trajectories
+                       (`python oracle/make_golden.py --baseline` writes only these)
 
 TEST INFRASTRUCTURE ONLY.
 """
@@ -29,6 +35,7 @@ import torch
 
 sys.modules.setdefault("kornia", types.ModuleType("kornia"))
 sys.path.insert(0, "/root/reference")
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
 
 from geocalib.camera import camera_models  # noqa: E402
 from geocalib.gravity import Gravity  # noqa: E402
@@ -208,9 +215,55 @@ def golden_init():
     np.savez_compressed(OUT / "init.npz", **out)
 
 
+def golden_baseline(name, model, B, h, w, seed, conf, iters=(1, 2, 3)):
+    """A BASELINE.json configuration at its real image size: recipe in, reference outputs out."""
+    from oracle import oracle  # the seeded input recipe only (render + numpy noise)
+
+    f, cam_gt, grav_gt = oracle.procedural_fields(model, B, h, w, seed)
+    save = dict(model=model, B=B, h=h, w=w, seed=seed, conf_keys=np.array(list(conf.keys())),
+                conf_vals=np.array([float(v) for v in conf.values()]), cam_gt=cam_gt, grav_gt=grav_gt,
+                checksums=oracle.field_checksums(f))
+    res = run_reference(model, f, conf)
+    save |= {f"out_{k}": v for k, v in res.items()}
+    for k in iters:
+        r = run_reference(model, f, {**conf, "num_steps": k, "early_stop": False})
+        save[f"it{k}_camera"] = r["camera"]
+        save[f"it{k}_gravity"] = r["gravity"]
+        save[f"it{k}_final_cost"] = r["final_cost"]
+    # iteration-0 system at the trivial initial estimate, fp64 (SURVEY 8d "Parity check")
+    opt = LMOptimizer({"camera_model": model, **conf}).eval()
+    data32 = {k: t(v) for k, v in f.items()}
+    cam0, grav0 = get_trivial_estimation(data32, camera_models[model])
+    save["init_camera"], save["init_gravity"] = cam0._data.numpy(), grav0.vec3d.numpy()
+    data = {k: t(v, True) for k, v in f.items()}
+    camera, gravity = camera_models[model](cam0._data.double()), Gravity(grav0.vec3d.double())
+    resid = opt.calculate_residuals(camera, gravity, data)
+    costs, weights = opt.calculate_costs(resid, data)
+    for basis, as_rpf in (("opt", False), ("rpf", True)):
+        G, H = opt.setup_system(camera, gravity, resid, weights, as_rpf=as_rpf)
+        save[f"G0_{basis}_f64"], save[f"H0_{basis}_f64"] = G.numpy(), H.numpy()
+    save["cost0_up_f64"] = costs["up_cost"].mean(-1).numpy()
+    save["cost0_lat_f64"] = costs["latitude_cost"].mean(-1).numpy()
+    np.savez_compressed(OUT / f"base_{name}.npz", **save)
+    print(name, "stop_at", res["stop_at"], "f", res["camera"][:, 3], "gt", cam_gt[:, 3])
+
+
+def baseline_cases():
+    fixed20 = {"num_steps": 20, "early_stop": False}
+    golden_baseline("config0_pinhole_320x240", "pinhole", 1, 240, 320, 7000, {"num_steps": 10, "early_stop": False})
+    golden_baseline("config1_pinhole_640x480", "pinhole", 4, 480, 640, 7001, fixed20)
+    golden_baseline("config1_pinhole_640x480_default", "pinhole", 2, 480, 640, 7002, {})
+    golden_baseline("config2_simple_radial_640x480", "simple_radial", 4, 480, 640, 7003, fixed20)
+    golden_baseline("config3_simple_divisional_1024", "simple_divisional", 2, 1024, 1024, 7004, fixed20)
+    golden_baseline("radial_640x480", "radial", 2, 480, 640, 7005, fixed20)
+
+
 def main():
     OUT.mkdir(parents=True, exist_ok=True)
     torch.manual_seed(0)
+    if "--baseline" in sys.argv:
+        baseline_cases()
+        return
     for i, m in enumerate(MODELS):
         golden_system(m, 100 + i)
     for i, m in enumerate(MODELS):
@@ -230,6 +283,7 @@ def main():
     golden_lm("shared_radial", "radial", 401, B=3, h=32, w=48, shared=True)
     golden_lm("shared_simple_divisional", "simple_divisional", 402, B=3, h=32, w=48, shared=True)
     golden_init()
+    baseline_cases()
 
 
 if __name__ == "__main__":

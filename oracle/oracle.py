@@ -140,6 +140,61 @@ def gravity_rp(g):
     return np.stack([roll, np.arcsin(g[..., 2])], -1)
 
 
+def gt_params(model, B, h, w, seed):
+    """Ground-truth cameras (B,8) / gravities (B,3) of the synthetic workload: roll, pitch
+    ~ U(-45, 45) deg, vfov ~ U(30, 90) deg (fisheye: U(60, 120)), k1 ~ U(-0.15, 0.15)
+    (simple_divisional: U(-0.4, -0.05))."""
+    rng = np.random.default_rng(seed)
+    roll = rng.uniform(-np.pi / 4, np.pi / 4, B)
+    pitch = rng.uniform(-np.pi / 4, np.pi / 4, B)
+    fish = model == "simple_divisional"
+    vfov = np.deg2rad(rng.uniform(60, 120, B) if fish else rng.uniform(30, 90, B))
+    fy = h / 2 / np.tan(vfov / 2)
+    k1 = np.zeros(B)
+    k2 = np.zeros(B)
+    if model in ("simple_radial", "radial"):
+        k1 = rng.uniform(-0.15, 0.15, B)
+    if model == "radial":
+        k2 = rng.uniform(-0.03, 0.03, B)
+    if fish:
+        k1 = rng.uniform(-0.4, -0.05, B)
+    cam = np.stack([np.full(B, w), np.full(B, h), fy, fy, np.full(B, w / 2), np.full(B, h / 2), k1, k2], -1)
+    sr, cr, sp, cp = np.sin(roll), np.cos(roll), np.sin(pitch), np.cos(pitch)
+    grav = np.stack([-sr * cp, -cr * cp, sp], -1)
+    return cam.astype(np.float32), grav.astype(np.float32)
+
+
+def procedural_fields(model, B, h, w, seed, sigma=0.02, conf_lo=0.2):
+    """Seeded synthetic predicted fields, reproducible from (model, B, h, w, seed) alone: GT render in
+    fp64 (rounded to fp32) + N(0, sigma^2) noise, up re-normalised, confidences ~ U(conf_lo, 1).
+
+    Used by oracle/make_golden.py to feed the REFERENCE at the BASELINE image sizes (only the recipe and
+    the reference's outputs are stored: the inputs would be 6-12 MB per case) and by the tests to
+    regenerate the same inputs; `field_checksums` guards the regeneration.
+    Returns (fields dict of float32 arrays, cam_gt (B,8), grav_gt (B,3))."""
+    cam, grav = gt_params(model, B, h, w, seed)
+    rng = np.random.default_rng(seed + 1)
+    up = np.empty((B, 2, h, w), np.float32)
+    lat = np.empty((B, 1, h, w), np.float32)
+    for b in range(B):
+        u, l = render(model, cam[b], grav[b], h, w, dtype=np.float64)
+        u = u + rng.normal(0, sigma, (2, h, w))
+        up[b] = (u / np.linalg.norm(u, axis=0, keepdims=True)).astype(np.float32)
+        lat[b] = (l + rng.normal(0, sigma, (1, h, w))).astype(np.float32)
+    uc = rng.uniform(conf_lo, 1, (B, h, w)).astype(np.float32)
+    lc = rng.uniform(conf_lo, 1, (B, h, w)).astype(np.float32)
+    return dict(up_field=up, latitude_field=lat, up_confidence=uc, latitude_confidence=lc), cam, grav
+
+
+def field_checksums(fields):
+    """Order-independent fp64 digests of the four field tensors (sum and sum of squares per tensor)."""
+    out = []
+    for k in ("up_field", "latitude_field", "up_confidence", "latitude_confidence"):
+        a = fields[k].astype(np.float64)
+        out += [a.sum(), (a * a).sum()]
+    return np.array(out)
+
+
 def trivial_init(batch, h, w, *, scales=None, prior_focal=None, prior_gravity=None,
                  prior_dist=None, dtype=np.float32):
     """Initial camera (B,8) / gravity (B,3): roll=pitch=0, f=0.7*max(h,w) via a vfov round trip."""

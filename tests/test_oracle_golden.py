@@ -106,3 +106,53 @@ def test_lm_trajectory_matches_reference(golden_dir, case):
         out = run_oracle_on_golden(g, conf={"num_steps": k, "early_stop": False})
         assert_params_close(out, g, prefix=f"it{k}_", tol=2e-5)
         np.testing.assert_allclose(out["final_cost"], g[f"it{k}_final_cost"], rtol=2e-4)
+
+
+# ----------------------------------------------------------------------------------------------
+# BASELINE.json configurations at their real image sizes (reference outputs; seeded input recipe)
+# ----------------------------------------------------------------------------------------------
+BASE_CASES = ["config0_pinhole_320x240", "config1_pinhole_640x480", "config1_pinhole_640x480_default",
+              "config2_simple_radial_640x480", "config3_simple_divisional_1024", "radial_640x480"]
+
+
+def load_base_case(golden_dir, case):
+    """Golden record + the regenerated inputs (checked against the stored digests)."""
+    g = _load(golden_dir, f"base_{case}.npz")
+    model = str(g["model"])
+    f, cam_gt, _ = oracle.procedural_fields(model, int(g["B"]), int(g["h"]), int(g["w"]), int(g["seed"]))
+    np.testing.assert_allclose(oracle.field_checksums(f), g["checksums"], rtol=1e-9,
+                               err_msg="regenerated inputs differ from the ones the reference saw")
+    np.testing.assert_array_equal(cam_gt, g["cam_gt"])
+    conf = {k: (v if k in ("lambda_", "atol", "rtol") else int(v))
+            for k, v in zip(g["conf_keys"].tolist(), g["conf_vals"].tolist())}
+    return g, model, f, conf
+
+
+@pytest.mark.parametrize("case", BASE_CASES)
+def test_baseline_size_lm_matches_reference(golden_dir, case):
+    g, model, f, conf = load_base_case(golden_dir, case)
+    g = dict(g, shared=False)
+    out = oracle.lm(model, f["up_field"], f["latitude_field"], f["up_confidence"], f["latitude_confidence"], conf=conf)
+    assert_params_close(out, g)
+    np.testing.assert_array_equal(out["stop_at"], g["out_stop_at"].astype(np.int32))
+    np.testing.assert_allclose(out["final_cost"], g["out_final_cost"], rtol=2e-4)
+    np.testing.assert_allclose(out["initial_cost"], g["out_initial_cost"], rtol=2e-4)
+    for k in (1, 2, 3):
+        o = oracle.lm(model, f["up_field"], f["latitude_field"], f["up_confidence"], f["latitude_confidence"],
+                      conf={**conf, "num_steps": k, "early_stop": False})
+        assert_params_close(o, g, prefix=f"it{k}_", tol=2e-5)
+
+
+@pytest.mark.parametrize("case", ["config1_pinhole_640x480", "config2_simple_radial_640x480",
+                                  "config3_simple_divisional_1024"])
+def test_baseline_size_iteration0_system(golden_dir, case):
+    """G, H and costs of iteration 0 (trivial initial estimate) in fp64 at full image size."""
+    g, model, f, _ = load_base_case(golden_dir, case)
+    for b in range(int(g["B"])):
+        for basis, rpf in (("opt", False), ("rpf", True)):
+            G, H, cost = oracle.system(model, g["init_camera"][b], g["init_gravity"][b], f["up_field"][b],
+                                       f["latitude_field"][b], f["up_confidence"][b], f["latitude_confidence"][b],
+                                       rpf_basis=rpf, dtype=np.float64)
+            assert _rel(G, g[f"G0_{basis}_f64"][b]) < 1e-9
+            assert _rel(H, g[f"H0_{basis}_f64"][b]) < 1e-9
+        assert abs(cost[0] / g["cost0_up_f64"][b] - 1) < 1e-9 and abs(cost[1] / g["cost0_lat_f64"][b] - 1) < 1e-9
