@@ -24,6 +24,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <mutex>
 #include <new>
 #include <vector>
 
@@ -78,6 +79,9 @@ struct PassArgs {
   // shared-intrinsics scratch
   float* schur;        // (B,SCHUR_STRIDE)
   gclm_result res;
+  // gclm_system (diagnostic): raw J^T W r / J^T W J / mean costs of the single pass, full columns
+  int final_rpf;       // basis of the final pass: 1 = (roll,pitch) + linear focal (covariance), 0 = LM basis
+  float *sys_g, *sys_h, *sys_cost;
 };
 
 __device__ __forceinline__ float4 ldg_stream(const float* p) {
@@ -244,6 +248,22 @@ __device__ __noinline__ void lm_step_image(const PassArgs& a, int b, const float
   constexpr int K = Dims<MODEL>::K, NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH;
   int sl = a.slot[b];
   if (a.is_final) {
+    if (a.sys_h) {  // gclm_system: hand the reduced system out as it is (full columns [g0 g1 f k..])
+      const float invN = 1.f / ((float)a.H * (float)a.Wt);
+      int idx = 0;
+      for (int i = 0; i < NF; i++)
+        for (int j = i; j < NF; j++) {
+          a.sys_h[((size_t)b * NF + i) * NF + j] = sums[idx];
+          a.sys_h[((size_t)b * NF + j) * NF + i] = sums[idx];
+          idx++;
+        }
+      if (a.sys_g) for (int i = 0; i < NF; i++) a.sys_g[(size_t)b * NF + i] = sums[NH + i];
+      if (a.sys_cost) {
+        a.sys_cost[b * 2] = sums[NH + NF] * (a.up_scale * a.up_scale) * invN;
+        a.sys_cost[b * 2 + 1] = sums[NH + NF + 1] * (a.lat_scale * a.lat_scale) * invN;
+      }
+      return;
+    }
     if (a.ctrl->stop) sl ^= 1;  // batch stop fired: the tentative update of that pass is dropped
     finalize_image<MODEL>(a, b, sums, sl);
     return;
@@ -568,7 +588,7 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
     int sl = a.slot[b];
     if (a.is_final && a.ctrl->stop) sl ^= 1;
     const float* Pb = a.P + ((size_t)b * 2 + sl) * PSTRIDE;
-    make_pass_const(Pb, Pb + 8, a.spherical != 0, a.log_focal != 0, a.is_final != 0, s_pc);
+    make_pass_const(Pb, Pb + 8, a.spherical != 0, a.log_focal != 0, a.is_final != 0 && a.final_rpf != 0, s_pc);
   }
   __syncthreads();
   const PassConst pc = s_pc;
@@ -965,6 +985,19 @@ struct gclm_handle {
   size_t stage_bytes = 0;
   cudaStream_t hstream[2] = {nullptr, nullptr};
   cudaEvent_t hevent[2] = {nullptr, nullptr};
+  cudaEvent_t hready[2] = {nullptr, nullptr};
+  // One handle = one scratch block: solves are serialised.  `mu` orders host threads, `last_done`
+  // (recorded at the end of every solve) orders solves enqueued on DIFFERENT streams (gclm.h contract).
+  std::mutex mu;
+  cudaEvent_t last_done = nullptr;
+  cudaStream_t last_stream = nullptr;
+  bool have_last = false;
+  // > 48 KB dynamic shared memory opt-in per kernel instantiation: a per-DEVICE attribute, so it lives in
+  // the per-device handle ([model][gen_d][full][pack])
+  size_t smem_configured[4][2][2][2] = {};
+#ifdef GCLM_TMA2D
+  gclm::TmaMaps maps;  // tensor maps of the current solve
+#endif
   // opt-in timing of the pass launches (gclm_pass_timing): one event pair per solve, ring of TIMED
   static constexpr int TIMED = 64;
   bool timing = false;
@@ -1053,6 +1086,35 @@ struct gclm_comm {
 
 namespace {
 
+// Every entry point runs on the handle's device and leaves the caller's current device untouched.
+struct DeviceGuard {
+  int prev = -1; bool changed = false, good = true;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+    if (prev != dev) { good = cudaSetDevice(dev) == cudaSuccess; changed = good; }
+  }
+  ~DeviceGuard() { if (changed && prev >= 0) cudaSetDevice(prev); }
+  bool ok() const { return good; }
+};
+
+// Serialises the solves of one handle: host mutex + (when the stream changes) a wait on the event the
+// previous solve recorded, so two solves never share the scratch block concurrently.
+struct SolveOrder {
+  gclm_handle* h; cudaStream_t s; std::unique_lock<std::mutex> lock;
+  SolveOrder(gclm_handle* h_, cudaStream_t s_) : h(h_), s(s_), lock(h_->mu) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    const bool capturing = cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+    if (h->have_last && h->last_stream != s && !capturing) cudaStreamWaitEvent(s, h->last_done, 0);
+  }
+  void done() {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone) return;
+    if (!h->last_done && cudaEventCreateWithFlags(&h->last_done, cudaEventDisableTiming) != cudaSuccess) return;
+    cudaEventRecord(h->last_done, s);
+    h->last_stream = s; h->have_last = true;
+  }
+};
+
 struct Layout {  // carve the scratch buffer
   size_t P, lam, prev, cost0, slot, flags, stop_at, tickets, ctrl, partials, schur, sinlat, repack, total;
 };
@@ -1107,6 +1169,7 @@ Layout make_layout(int B, int max_tiles, size_t pixels, bool repack) {
 
 int ensure_scratch(gclm_handle* h, size_t bytes) {
   if (bytes <= h->scratch_bytes) return GCLM_OK;
+  if (h->have_last) cudaEventSynchronize(h->last_done);  // a queued solve may still use the old block
   if (h->scratch) cudaFree(h->scratch);
   h->scratch = nullptr; h->scratch_bytes = 0;
   CUDA_TRY(h, cudaMalloc(&h->scratch, bytes));
@@ -1120,10 +1183,9 @@ int max_tiles_for(int H, int W) {
 }
 
 #ifdef GCLM_TMA2D
-TmaMaps g_maps;  // tensor maps of the current solve (a handle is single-threaded by contract)
-
 // 2-D tensor maps (width W, all rows of all images of a plane stacked) for the TMA build.
-bool encode_maps(const PassArgs& a) {
+bool encode_maps(gclm_handle* h, const PassArgs& a) {
+  TmaMaps& g_maps = h->maps;
   typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1150,33 +1212,33 @@ bool encode_maps(const PassArgs& a) {
 #endif
 
 template <int MODEL, bool GEN_D, bool FULL, bool PACK>
-void launch_one(const PassArgs& a, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
-  static size_t configured = 0;  // opt in to > 48 KB of dynamic shared memory once per instantiation
+void launch_one(gclm_handle* h, const PassArgs& a, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
+  size_t& configured = h->smem_configured[MODEL][GEN_D][FULL][PACK];  // per device (the handle's)
   if (smem > configured) {
     cudaFuncSetAttribute(lm_pass_kernel<MODEL, GEN_D, FULL, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
 #ifdef GCLM_TMA2D
-  lm_pass_kernel<MODEL, GEN_D, FULL, PACK><<<grid, block, smem, s>>>(a, g_maps);
+  lm_pass_kernel<MODEL, GEN_D, FULL, PACK><<<grid, block, smem, s>>>(a, h->maps);
 #else
   lm_pass_kernel<MODEL, GEN_D, FULL, PACK><<<grid, block, smem, s>>>(a);
 #endif
 }
 
 template <int MODEL, bool PACK>
-void launch_pass_model(const PassArgs& a, bool gen_d, bool full, dim3 grid, dim3 block, cudaStream_t s) {
+void launch_pass_model(gclm_handle* h, const PassArgs& a, bool gen_d, bool full, dim3 grid, dim3 block, cudaStream_t s) {
 #ifdef GCLM_TMA2D
   const size_t smem = full ? (size_t)(block.x / 32) * (TMA_STAGES * 5 * TMA_ROWS * 512 + TMA_STAGES * 8) + 128 : 0;
-  if (full && !encode_maps(a)) return;  // leaves the sticky error for cudaGetLastError-less callers: results stay unset
+  if (full && !encode_maps(h, a)) return;  // leaves the sticky error for cudaGetLastError-less callers: results stay unset
 #else
   const size_t smem = full ? (size_t)RING_STAGES * 5 * block.x * 16 + (size_t)(block.x / 32) * RING_STAGES * 8 : 0;
 #endif
   if (gen_d) {
-    if (full) launch_one<MODEL, true, true, PACK>(a, grid, block, smem, s);
-    else launch_one<MODEL, true, false, PACK>(a, grid, block, 0, s);
+    if (full) launch_one<MODEL, true, true, PACK>(h, a, grid, block, smem, s);
+    else launch_one<MODEL, true, false, PACK>(h, a, grid, block, 0, s);
   } else {
-    if (full) launch_one<MODEL, false, true, PACK>(a, grid, block, smem, s);
-    else launch_one<MODEL, false, false, PACK>(a, grid, block, 0, s);
+    if (full) launch_one<MODEL, false, true, PACK>(h, a, grid, block, smem, s);
+    else launch_one<MODEL, false, false, PACK>(h, a, grid, block, 0, s);
   }
 }
 
@@ -1187,20 +1249,20 @@ bool use_packed() {
   return v != 0;
 }
 
-void launch_pass(const PassArgs& a, bool gen_d, bool full, dim3 grid, dim3 block, cudaStream_t s) {
+void launch_pass(gclm_handle* h, const PassArgs& a, bool gen_d, bool full, dim3 grid, dim3 block, cudaStream_t s) {
   if (use_packed()) {
     switch (a.model) {
-      case PINHOLE: launch_pass_model<PINHOLE, true>(a, gen_d, full, grid, block, s); break;
-      case SIMPLE_RADIAL: launch_pass_model<SIMPLE_RADIAL, true>(a, gen_d, full, grid, block, s); break;
-      case RADIAL: launch_pass_model<RADIAL, true>(a, gen_d, full, grid, block, s); break;
-      default: launch_pass_model<SIMPLE_DIVISIONAL, true>(a, gen_d, full, grid, block, s); break;
+      case PINHOLE: launch_pass_model<PINHOLE, true>(h, a, gen_d, full, grid, block, s); break;
+      case SIMPLE_RADIAL: launch_pass_model<SIMPLE_RADIAL, true>(h, a, gen_d, full, grid, block, s); break;
+      case RADIAL: launch_pass_model<RADIAL, true>(h, a, gen_d, full, grid, block, s); break;
+      default: launch_pass_model<SIMPLE_DIVISIONAL, true>(h, a, gen_d, full, grid, block, s); break;
     }
   } else {
     switch (a.model) {
-      case PINHOLE: launch_pass_model<PINHOLE, false>(a, gen_d, full, grid, block, s); break;
-      case SIMPLE_RADIAL: launch_pass_model<SIMPLE_RADIAL, false>(a, gen_d, full, grid, block, s); break;
-      case RADIAL: launch_pass_model<RADIAL, false>(a, gen_d, full, grid, block, s); break;
-      default: launch_pass_model<SIMPLE_DIVISIONAL, false>(a, gen_d, full, grid, block, s); break;
+      case PINHOLE: launch_pass_model<PINHOLE, false>(h, a, gen_d, full, grid, block, s); break;
+      case SIMPLE_RADIAL: launch_pass_model<SIMPLE_RADIAL, false>(h, a, gen_d, full, grid, block, s); break;
+      case RADIAL: launch_pass_model<RADIAL, false>(h, a, gen_d, full, grid, block, s); break;
+      default: launch_pass_model<SIMPLE_DIVISIONAL, false>(h, a, gen_d, full, grid, block, s); break;
     }
   }
 }
@@ -1263,6 +1325,7 @@ PassArgs make_args(gclm_handle* h, const gclm_problem* p, const gclm_options* o,
   a.partials = reinterpret_cast<float*>(base + L.partials);
   a.schur = reinterpret_cast<float*>(base + L.schur);
   a.res = *r;
+  a.final_rpf = 1;
   return a;
 }
 
@@ -1328,7 +1391,6 @@ int gclm_create(int device, gclm_handle** out) {
   gclm_handle* h = new (std::nothrow) gclm_handle();
   if (!h) return GCLM_ERR_OUT_OF_MEMORY;
   h->device = device;
-  CUDA_TRY(h, cudaSetDevice(device));
   int sms = 0;
   if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0)
     h->num_sms = sms;
@@ -1338,13 +1400,15 @@ int gclm_create(int device, gclm_handle** out) {
 
 int gclm_destroy(gclm_handle* h) {
   if (!h) return GCLM_OK;
-  cudaSetDevice(h->device);
+  DeviceGuard guard(h->device);
   if (h->scratch) cudaFree(h->scratch);
   for (int i = 0; i < 2; i++) {
     if (h->stage[i]) cudaFree(h->stage[i]);
     if (h->hstream[i]) cudaStreamDestroy(h->hstream[i]);
     if (h->hevent[i]) cudaEventDestroy(h->hevent[i]);
+    if (h->hready[i]) cudaEventDestroy(h->hready[i]);
   }
+  if (h->last_done) cudaEventDestroy(h->last_done);
   for (int i = 0; i < gclm_handle::TIMED; i++)
     for (int k = 0; k < 2; k++)
       if (h->tev[i][k]) cudaEventDestroy(h->tev[i][k]);
@@ -1354,7 +1418,10 @@ int gclm_destroy(gclm_handle* h) {
 
 int gclm_reserve(gclm_handle* h, int batch, int height, int width) {
   if (!h || batch <= 0 || height <= 0 || width <= 0) return GCLM_ERR_INVALID_ARGUMENT;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  if (!guard.ok()) return GCLM_ERR_CUDA;
+  std::lock_guard<std::mutex> lk(h->mu);
+  if (h->have_last) cudaEventSynchronize(h->last_done);  // never free scratch a queued solve still uses
   const Layout L = make_layout(batch, max_tiles_for(height, width), (size_t)height * padded_width(width), width % 4 != 0);
   return ensure_scratch(h, L.total);
 }
@@ -1381,7 +1448,8 @@ int gclm_pass_timing(gclm_handle* h, int enable) {
 
 int gclm_pass_time(gclm_handle* h, double* total_ms, int64_t* passes) {
   if (!h || !total_ms || !passes) return GCLM_ERR_INVALID_ARGUMENT;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  if (!guard.ok()) return GCLM_ERR_CUDA;
   *total_ms = 0.0; *passes = 0;
   const int64_t n = std::min<int64_t>(h->tcount, gclm_handle::TIMED);
   for (int64_t i = 0; i < n; i++) {
@@ -1399,8 +1467,10 @@ int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt
   int st = validate(prob, opt);
   if (st != GCLM_OK) return st;
   if (prob->shared_intrinsics) return GCLM_ERR_INVALID_ARGUMENT;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  if (!guard.ok()) return GCLM_ERR_CUDA;
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  SolveOrder order(h, s);
   const TileCfg t = tile_config(prob->batch, prob->height, padded_width(prob->width), h->num_sms, opt->rows_per_tile,
                                 max_warps_for(prob->camera_model, use_packed()));
   const Layout L = make_layout(prob->batch, std::max(t.tiles_per_image, max_tiles_for(prob->height, prob->width)),
@@ -1416,13 +1486,46 @@ int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt
   PassTimer timer(h, s, opt->num_steps + 1);
   for (int it = 0; it < opt->num_steps; it++) {
     a.pass = it; a.is_final = 0;
-    launch_pass(a, !opt->use_log_focal, full, grid, block, s);
+    launch_pass(h, a, !opt->use_log_focal, full, grid, block, s);
     h->launches++;
   }
   a.pass = opt->num_steps; a.is_final = 1;
-  launch_pass(a, true, full, grid, block, s);
+  launch_pass(h, a, true, full, grid, block, s);
   h->launches++;
   timer.stop();
+  order.done();
+  CUDA_TRY(h, cudaGetLastError());
+  return GCLM_OK;
+}
+
+int gclm_system(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt, int rpf_basis,
+                float* gradient, float* hessian, float* costs, void* cuda_stream) {
+  if (!h || !hessian) return GCLM_ERR_INVALID_ARGUMENT;
+  int st = validate(prob, opt);
+  if (st != GCLM_OK) return st;
+  DeviceGuard guard(h->device);
+  if (!guard.ok()) return GCLM_ERR_CUDA;
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  SolveOrder order(h, s);
+  const TileCfg t = tile_config(prob->batch, prob->height, padded_width(prob->width), h->num_sms, opt->rows_per_tile,
+                                max_warps_for(prob->camera_model, use_packed()));
+  const Layout L = make_layout(prob->batch, std::max(t.tiles_per_image, max_tiles_for(prob->height, prob->width)),
+                               (size_t)prob->height * padded_width(prob->width), needs_repack(prob));
+  st = ensure_scratch(h, L.total);
+  if (st != GCLM_OK) return st;
+  gclm_result none;
+  memset(&none, 0, sizeof(none));
+  PassArgs a = make_args(h, prob, opt, &none, t, L);
+  a.num_steps = 0; a.pass = 0; a.is_final = 1;
+  a.final_rpf = rpf_basis != 0;
+  a.sys_g = gradient; a.sys_h = hessian; a.sys_cost = costs;
+  const bool full = a.up && a.lat && a.uconf && a.lconf;
+  lm_init_kernel<<<(prob->batch + 127) / 128, 128, 0, s>>>(a, prob->camera_init, prob->gravity_init);
+  launch_sin_plane(h, prob, a, s);
+  const dim3 grid((unsigned)((size_t)prob->batch * t.tiles_per_image)), block(t.nwarps * 32);
+  launch_pass(h, a, rpf_basis ? true : !opt->use_log_focal, full, grid, block, s);
+  h->launches += 2;
+  order.done();
   CUDA_TRY(h, cudaGetLastError());
   return GCLM_OK;
 }
@@ -1438,8 +1541,10 @@ int gclm_solve_shared(gclm_handle* h, const gclm_problem* prob, const gclm_optio
     nccl = nccl_api();
     if (!nccl || !comm->comm) return GCLM_ERR_NCCL;
   }
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  if (!guard.ok()) return GCLM_ERR_CUDA;
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  SolveOrder order(h, s);
   const TileCfg t = tile_config(prob->batch, prob->height, padded_width(prob->width), h->num_sms, opt->rows_per_tile,
                                 max_warps_for(prob->camera_model, use_packed()));
   const Layout L = make_layout(prob->batch, std::max(t.tiles_per_image, max_tiles_for(prob->height, prob->width)),
@@ -1459,7 +1564,7 @@ int gclm_solve_shared(gclm_handle* h, const gclm_problem* prob, const gclm_optio
   PassTimer timer(h, s, opt->num_steps + 1);  // here the bracket also holds the O(B) Schur kernels
   for (int it = 0; it < opt->num_steps; it++) {
     a.pass = it; a.is_final = 0;
-    launch_pass(a, !opt->use_log_focal, full, grid, block, s);
+    launch_pass(h, a, !opt->use_log_focal, full, grid, block, s);
     P2PArgs pp;
     memset(&pp, 0, sizeof(pp));
     const bool p2p = comm && comm->world > 1 && comm->p2p_ready;
@@ -1486,9 +1591,10 @@ int gclm_solve_shared(gclm_handle* h, const gclm_problem* prob, const gclm_optio
     h->launches += 4;
   }
   a.pass = opt->num_steps; a.is_final = 1;
-  launch_pass(a, true, full, grid, block, s);
+  launch_pass(h, a, true, full, grid, block, s);
   h->launches++;
   timer.stop();
+  order.done();
   CUDA_TRY(h, cudaGetLastError());
   return GCLM_OK;
 }
@@ -1508,7 +1614,8 @@ int gclm_comm_create(const void* unique_id, int world_size, int rank, int device
   *out = nullptr;
   NcclApi* nccl = nccl_api();
   if (!nccl) return GCLM_ERR_NCCL;
-  if (cudaSetDevice(device) != cudaSuccess) return GCLM_ERR_CUDA;
+  DeviceGuard guard(device);
+  if (!guard.ok()) return GCLM_ERR_CUDA;
   gclm_comm* c = new (std::nothrow) gclm_comm();
   if (!c) return GCLM_ERR_OUT_OF_MEMORY;
   c->world = world_size; c->rank = rank; c->device = device;
@@ -1521,7 +1628,7 @@ int gclm_comm_create(const void* unique_id, int world_size, int rank, int device
 
 int gclm_comm_destroy(gclm_comm* c) {
   if (!c) return GCLM_OK;
-  cudaSetDevice(c->device);
+  DeviceGuard guard(c->device);
   for (int r = 0; r < c->world && r < P2P_MAX_RANKS; r++)
     if (r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
   if (c->local) cudaFree(c->local);
@@ -1535,7 +1642,8 @@ int gclm_comm_p2p_export(gclm_comm* c, void* handle_out) {
   if (!c || !handle_out) return GCLM_ERR_INVALID_ARGUMENT;
   if (c->world > P2P_MAX_RANKS) return GCLM_ERR_UNSUPPORTED;
   static_assert(sizeof(cudaIpcMemHandle_t) <= GCLM_IPC_HANDLE_BYTES, "IPC handle size");
-  if (cudaSetDevice(c->device) != cudaSuccess) return GCLM_ERR_CUDA;
+  DeviceGuard guard(c->device);
+  if (!guard.ok()) return GCLM_ERR_CUDA;
   if (!c->local) {
     if (cudaMalloc(reinterpret_cast<void**>(&c->local), sizeof(P2PBuf)) != cudaSuccess) return GCLM_ERR_OUT_OF_MEMORY;
     if (cudaMemset(c->local, 0, sizeof(P2PBuf)) != cudaSuccess) return GCLM_ERR_CUDA;
@@ -1557,7 +1665,8 @@ int gclm_comm_p2p_disable(gclm_comm* c) {
 int gclm_comm_p2p_attach(gclm_comm* c, const void* handles) {
   if (!c || !handles || !c->local) return GCLM_ERR_INVALID_ARGUMENT;
   if (c->world > P2P_MAX_RANKS) return GCLM_ERR_UNSUPPORTED;
-  if (cudaSetDevice(c->device) != cudaSuccess) return GCLM_ERR_CUDA;
+  DeviceGuard guard(c->device);
+  if (!guard.ok()) return GCLM_ERR_CUDA;
   for (int r = 0; r < c->world; r++) {
     if (r == c->rank) { c->peer[r] = c->local; continue; }
     cudaIpcMemHandle_t hnd;
@@ -1580,7 +1689,8 @@ int gclm_solve_host(gclm_handle* h, const gclm_problem* prob, const gclm_options
   int st = validate(prob, opt);
   if (st != GCLM_OK) return st;
   if (prob->shared_intrinsics) return GCLM_ERR_UNSUPPORTED;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  if (!guard.ok()) return GCLM_ERR_CUDA;
   const int B = prob->batch, H = prob->height, W = prob->width;
   const size_t N = (size_t)H * W;
   const int chunk = std::max(1, std::min(chunk_images > 0 ? chunk_images : 128, B));
@@ -1598,10 +1708,10 @@ int gclm_solve_host(gclm_handle* h, const gclm_problem* prob, const gclm_options
   for (int i = 0; i < 2; i++) {
     if (!h->hstream[i]) CUDA_TRY(h, cudaStreamCreateWithFlags(&h->hstream[i], cudaStreamNonBlocking));
     if (!h->hevent[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&h->hevent[i], cudaEventDisableTiming));
+    if (!h->hready[i]) CUDA_TRY(h, cudaEventCreateWithFlags(&h->hready[i], cudaEventDisableTiming));
   }
   cudaStream_t s_copy = h->hstream[0], s_comp = h->hstream[1];
-  cudaEvent_t ready[2], freed[2] = {h->hevent[0], h->hevent[1]};
-  for (int i = 0; i < 2; i++) CUDA_TRY(h, cudaEventCreateWithFlags(&ready[i], cudaEventDisableTiming));
+  cudaEvent_t ready[2] = {h->hready[0], h->hready[1]}, freed[2] = {h->hevent[0], h->hevent[1]};  // handle-owned
   st = gclm_reserve(h, chunk, H, W);
   int rc = st;
   for (int s0 = 0, i = 0; s0 < B && rc == GCLM_OK; s0 += chunk, i++) {
@@ -1651,7 +1761,6 @@ int gclm_solve_host(gclm_handle* h, const gclm_problem* prob, const gclm_options
   }
   cudaError_t e = cudaStreamSynchronize(s_comp);
   cudaStreamSynchronize(s_copy);
-  for (int i = 0; i < 2; i++) cudaEventDestroy(ready[i]);
   if (rc != GCLM_OK) return rc;
   if (e != cudaSuccess) { snprintf(h->last_error, sizeof(h->last_error), "%s", cudaGetErrorString(e)); return GCLM_ERR_CUDA; }
   return GCLM_OK;
@@ -1663,7 +1772,8 @@ int gclm_render_fields(gclm_handle* h, int batch, int height, int width, int cam
                        float* latitude_confidence, void* cuda_stream) {
   if (!h || batch <= 0 || height <= 0 || width <= 0 || !camera || !gravity) return GCLM_ERR_INVALID_ARGUMENT;
   if (camera_model < 0 || camera_model > 3) return GCLM_ERR_INVALID_ARGUMENT;
-  CUDA_TRY(h, cudaSetDevice(h->device));
+  DeviceGuard guard(h->device);
+  if (!guard.ok()) return GCLM_ERR_CUDA;
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
   const size_t total = (size_t)batch * height * width;
   const unsigned blocks = (unsigned)((total + 255) / 256);

@@ -132,17 +132,45 @@ class Engine:
         res = Result(**{k: out[k].data_ptr() for k in
                         ("camera", "gravity", "covariance", "uncertainty", "costs", "stop_at", "status", "hessian_rpf")})
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-        with torch.cuda.device(dev):
-            if shared_intrinsics:
-                comm_h = getattr(comm, "handle", comm)
-                st = self.lib.gclm_solve_shared(self._h, ctypes.byref(prob), ctypes.byref(opt),
-                                                ctypes.byref(res), comm_h, stream)
-                _lib.check(st, "gclm_solve_shared")
-            else:
-                st = self.lib.gclm_solve(self._h, ctypes.byref(prob), ctypes.byref(opt),
-                                         ctypes.byref(res), stream)
-                _lib.check(st, "gclm_solve")
+        # the library runs on its handle's device and restores the caller's current device (DeviceGuard)
+        if shared_intrinsics:
+            comm_h = getattr(comm, "handle", comm)
+            st = self.lib.gclm_solve_shared(self._h, ctypes.byref(prob), ctypes.byref(opt),
+                                            ctypes.byref(res), comm_h, stream)
+            _lib.check(st, "gclm_solve_shared")
+        else:
+            st = self.lib.gclm_solve(self._h, ctypes.byref(prob), ctypes.byref(opt),
+                                     ctypes.byref(res), stream)
+            _lib.check(st, "gclm_solve")
         return out
+
+    # ------------------------------------------------------------------------------------------
+    def system(self, camera_model: str, up_field, latitude_field, up_confidence, latitude_confidence,
+               camera: torch.Tensor, gravity: torch.Tensor, *, options: Optional[Options] = None,
+               rpf_basis: bool = False):
+        """gclm_system: (G (B,NF), H (B,NF,NF), costs (B,2)) of one pass at the given parameters
+        (reference: LMOptimizer.setup_system + calculate_costs, lm_optimizer.py:276-315,387-461)."""
+        ref = up_field if up_field is not None else latitude_field
+        dev = ref.device
+        B, _, H, W = ref.shape
+        opt = options if options is not None else _lib.default_options()
+        nf = 3 + NUM_DIST[camera_model]
+        prob = Problem(
+            batch=B, height=H, width=W, camera_model=CAMERA_MODEL_IDS[camera_model],
+            up_field=_dev_ptr(up_field, (B, 2, H, W), "up_field", dev),
+            latitude_field=_dev_ptr(latitude_field, (B, 1, H, W), "latitude_field", dev),
+            up_confidence=_dev_ptr(up_confidence, (B, H, W), "up_confidence", dev),
+            latitude_confidence=_dev_ptr(latitude_confidence, (B, H, W), "latitude_confidence", dev),
+            camera_init=_dev_ptr(camera, (B, 8), "camera", dev),
+            gravity_init=_dev_ptr(gravity, (B, 3), "gravity", dev),
+            estimate_gravity=1, estimate_focal=1, estimate_dist=1, shared_intrinsics=0,
+        )
+        f32 = dict(device=dev, dtype=torch.float32)
+        G, Hm, c = torch.zeros((B, nf), **f32), torch.zeros((B, nf, nf), **f32), torch.zeros((B, 2), **f32)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(self.lib.gclm_system(self._h, ctypes.byref(prob), ctypes.byref(opt), int(bool(rpf_basis)),
+                                        G.data_ptr(), Hm.data_ptr(), c.data_ptr(), stream), "gclm_system")
+        return G, Hm, c
 
     # ------------------------------------------------------------------------------------------
     def render_fields(self, camera_model: str, camera: torch.Tensor, gravity: torch.Tensor,
@@ -210,7 +238,6 @@ class Engine:
             }
         res = Result(**{k: out[k].data_ptr() for k in
                         ("camera", "gravity", "covariance", "uncertainty", "costs", "stop_at", "status", "hessian_rpf")})
-        with torch.cuda.device(self.device):
-            _lib.check(self.lib.gclm_solve_host(self._h, ctypes.byref(prob), ctypes.byref(opt),
-                                                ctypes.byref(res), int(chunk_images)), "gclm_solve_host")
+        _lib.check(self.lib.gclm_solve_host(self._h, ctypes.byref(prob), ctypes.byref(opt),
+                                            ctypes.byref(res), int(chunk_images)), "gclm_solve_host")
         return out

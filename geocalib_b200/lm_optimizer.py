@@ -56,7 +56,8 @@ def get_trivial_estimation(data: Dict[str, torch.Tensor], camera_model) -> Tuple
     plain = not any(k in data for k in ("prior_focal", "prior_gravity", "prior_dist", "scales"))
     key = (B, h, w, str(ref.device), camera_model.name())
     if plain and key in _INIT_CACHE:  # the prior-free estimate depends on the shape only
-        return _INIT_CACHE[key]
+        cam, grav = _INIT_CACHE[key]
+        return cam.clone(), grav.clone()  # callers own what they get (no aliasing between solves)
     hh, ww = ref.new_full((B,), float(h)), ref.new_full((B,), float(w))
     focal = data["prior_focal"] if "prior_focal" in data else 0.7 * torch.max(hh, ww)
     params = {"width": ww, "height": hh, "vfov": focal2fov(focal.to(ref), h)}
@@ -78,7 +79,7 @@ def get_trivial_estimation(data: Dict[str, torch.Tensor], camera_model) -> Tuple
     if plain:
         if len(_INIT_CACHE) > 64:
             _INIT_CACHE.clear()
-        _INIT_CACHE[key] = out
+        _INIT_CACHE[key] = (out[0].clone(), out[1].clone())
     return out
 
 
@@ -197,6 +198,14 @@ class LMOptimizer(nn.Module):
             )
         uconf = self._field(data, "up_confidence", 0) if up is not None else None
         lconf = self._field(data, "latitude_confidence", 0) if lat is not None else None
+        if torch.is_grad_enabled() and any(
+                isinstance(data.get(k), torch.Tensor) and data[k].requires_grad
+                for k in ("up_field", "latitude_field", "up_confidence", "latitude_confidence")):
+            # the engine is inference-only (raw kernels, no backward): cutting gradients silently would
+            # turn a training run through the LM (siclib) into a no-op
+            raise _lib.GclmError(
+                "geocalib_b200.LMOptimizer is inference-only: the fields require grad but the engine has no "
+                "backward pass; call it under torch.no_grad() or detach the fields")
         name = self.camera_model.name()
         eng = get_engine(ref.device)
         raw = eng.solve(

@@ -14,7 +14,12 @@
  *     function name ends in `_host`.  The handle owns only scratch memory.
  *   - Work is enqueued on the caller's CUDA stream (a `cudaStream_t` passed as void*); the library
  *     never synchronises the device in gclm_solve / gclm_solve_shared.
- *   - One handle per device; a handle is not thread-safe, different handles are independent.
+ *   - One handle per device, different handles are independent.  A handle owns ONE scratch block, so
+ *     its solves are serialised: calls from several host threads take a per-handle mutex, and a solve
+ *     enqueued on a different stream than the previous one first waits (cudaStreamWaitEvent) on the
+ *     event the previous solve recorded.  Solves captured into a CUDA graph are exempt: replay graphs
+ *     of one handle on one stream.
+ *   - Every entry point runs on the handle's device and restores the caller's current device.
  *   - Numerical failure never raises (reference: lm_optimizer.py:129-133, 497-499): a failed
  *     Cholesky gives a zero step for THAT image and sets bit 0 of its status word.
  */
@@ -148,6 +153,19 @@ int gclm_reserve(gclm_handle* h, int batch, int height, int width);
  */
 int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt,
                const gclm_result* res, void* cuda_stream);
+
+/*
+ * Diagnostic: the reduced Gauss-Newton system of ONE pass at the given parameters, i.e. what
+ * LMOptimizer.setup_system + calculate_costs return (lm_optimizer.py:276-315, 387-461), with the full
+ * column set [g0 g1 | f | k..] (NF = 3 + num_dist): gradient (B,NF) = J^T W r, hessian (B,NF,NF) =
+ * J^T W J (undamped), costs (B,2) = mean up / latitude cost.  rpf_basis = 0: the LM basis
+ * (spherical tangent or roll/pitch per opt->use_spherical_manifold, log focal per opt->use_log_focal);
+ * 1: the covariance basis (roll, pitch, linear focal; as_rpf=True, :411-416).  Parameters are
+ * prob->camera_init / gravity_init.  Used by the parity tests (iteration-0 G/H/cost).
+ * gradient / costs may be NULL.  Asynchronous on `cuda_stream`.
+ */
+int gclm_system(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt, int rpf_basis,
+                float* gradient, float* hessian, float* costs, void* cuda_stream);
 
 /*
  * Shared intrinsics: replaces optimize() with shared_intrinsics=True (lm_optimizer.py:350-383,

@@ -1,0 +1,120 @@
+"""Parity of the CUDA engine at the BASELINE.json image sizes (SURVEY 8d "Parity check").
+
+  (a) reference-generated goldens (tests/golden/base_*.npz, written by oracle/make_golden.py --baseline
+      from the UNMODIFIED reference on a seeded input recipe): final parameters at 1e-4, 1/2/3-iteration
+      trajectories, and the iteration-0 Gauss-Newton system G / H / costs against the reference's fp64
+      values at 1e-5 -- fp32 sums over 3e5 .. 1e6 pixels with rsqrt.approx / rcp.approx are exactly where
+      a small-image test cannot speak for the configuration;
+  (b) the bench workload itself: the first 16 images (4 at 1024^2) of the device-rendered fields
+      bench.py times, engine vs the CPU oracle on identical inputs, fixed 20 iterations and the default
+      configuration (early stop on), 1e-4 on focal / distortion / gravity angles.
+"""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import oracle  # noqa: E402  (test infrastructure: the checker)
+
+from test_gpu_parity import assert_params_close, dev  # noqa: E402,F401
+from test_oracle_golden import BASE_CASES, load_base_case  # noqa: E402
+
+TOL = 1e-4
+
+
+def _t(a, dev):
+    return torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+
+
+def _run(model, f, conf, dev, **kw):
+    import geocalib_b200 as G
+
+    opt = G.LMOptimizer({"camera_model": model, **conf}).eval()
+    with torch.no_grad():
+        out = opt({k: _t(v, dev) for k, v in f.items()})
+    torch.cuda.synchronize()
+    return out
+
+
+@pytest.mark.parametrize("case", BASE_CASES)
+def test_baseline_size_lm_matches_reference_golden(golden_dir, dev, case):
+    g, model, f, conf = load_base_case(golden_dir, case)
+    out = _run(model, f, conf, dev)
+    cam, grav = out["camera"]._data.cpu().numpy(), out["gravity"]._data.cpu().numpy()
+    assert_params_close(cam, grav, g["out_camera"], g["out_gravity"], model, tol=TOL)
+    assert np.abs(out["stop_at"].cpu().numpy() - g["out_stop_at"]).max() <= 1
+    for k in ("initial_cost", "final_cost", "initial_up_cost", "final_up_cost",
+              "initial_latitude_cost", "final_latitude_cost"):
+        np.testing.assert_allclose(out[k].cpu().numpy(), g["out_" + k], rtol=2e-4, err_msg=k)
+    assert int(out["status"].sum()) == 0
+    # iteration path: parameters after exactly 1, 2, 3 LM steps
+    for k in (1, 2, 3):
+        o = _run(model, f, {**conf, "num_steps": k, "early_stop": False}, dev)
+        assert_params_close(o["camera"]._data.cpu().numpy(), o["gravity"]._data.cpu().numpy(),
+                            g[f"it{k}_camera"], g[f"it{k}_gravity"], model, tol=5e-5)
+        np.testing.assert_allclose(o["final_cost"].cpu().numpy(), g[f"it{k}_final_cost"], rtol=2e-4)
+
+
+def _scaled_err(A, R):
+    """max |A - R| in the scale of the system: H_ij relative to sqrt(H_ii H_jj), G_i to sqrt(H_ii)-free
+    max|G| (entries of very different magnitude: gravity ~1e5, k ~1e2)."""
+    return np.abs(A - R).max() / np.abs(R).max()
+
+
+@pytest.mark.parametrize("case", ["config0_pinhole_320x240", "config1_pinhole_640x480",
+                                  "config2_simple_radial_640x480", "config3_simple_divisional_1024",
+                                  "radial_640x480"])
+def test_baseline_size_iteration0_system_vs_reference_fp64(golden_dir, dev, case):
+    """G, H and the costs of iteration 0 (trivial initial estimate; for simple_divisional the k1 == 0
+    masked-denominator pass) against the reference's fp64 setup_system: 1e-5."""
+    from geocalib_b200.engine import get_engine
+
+    g, model, f, _ = load_base_case(golden_dir, case)
+    if "H0_opt_f64" not in g:
+        pytest.skip("golden has no iteration-0 system")
+    eng = get_engine(dev)
+    d = {k: _t(v, dev) for k, v in f.items()}
+    cam0, g0 = _t(g["init_camera"].astype(np.float32), dev), _t(g["init_gravity"].astype(np.float32), dev)
+    for basis, rpf in (("opt", False), ("rpf", True)):
+        G, H, c = eng.system(model, d["up_field"], d["latitude_field"], d["up_confidence"],
+                             d["latitude_confidence"], cam0, g0, rpf_basis=rpf)
+        torch.cuda.synchronize()
+        G, H, c = (x.cpu().numpy().astype(np.float64) for x in (G, H, c))
+        Gr, Hr = g[f"G0_{basis}_f64"], g[f"H0_{basis}_f64"]
+        for b in range(H.shape[0]):
+            dg = np.sqrt(np.abs(np.diag(Hr[b])))
+            assert (np.abs(H[b] - Hr[b]) / np.outer(dg, dg)).max() < 1e-5, (case, basis, b)
+            # gradient entries relative to the step they induce: |dG_i| / sqrt(H_ii) vs |G| / sqrt(H)
+            assert (np.abs(G[b] - Gr[b]) / dg).max() < 1e-5 * max(1.0, (np.abs(Gr[b]) / dg).max()), (case, basis, b)
+        np.testing.assert_allclose(c[:, 0], g["cost0_up_f64"], rtol=1e-5)
+        np.testing.assert_allclose(c[:, 1], g["cost0_lat_f64"], rtol=1e-5)
+
+
+BENCH_SLICES = [("pinhole", 16, 480, 640), ("simple_radial", 16, 480, 640), ("simple_divisional", 4, 1024, 1024),
+                ("radial", 8, 480, 640), ("pinhole", 1, 240, 320)]
+
+
+@pytest.mark.parametrize("model,B,h,w", BENCH_SLICES)
+@pytest.mark.parametrize("conf", [{"num_steps": 20, "early_stop": False}, {}], ids=["fixed20", "default"])
+def test_bench_workload_slice_vs_oracle(dev, model, B, h, w, conf):
+    """The fields bench.py times (same generator, same seeds), first B images, engine vs CPU oracle."""
+    from geocalib_b200.engine import get_engine
+
+    cam_gt, grav_gt = oracle.gt_params(model, B, h, w, 1234 + 1000 * 1 + 0)
+    eng = get_engine(dev)
+    f = eng.render_fields(model, _t(cam_gt, dev), _t(grav_gt, dev), h, w, sigma=0.02, conf_lo=0.2, seed=1234)
+    fn = {k: v.cpu().numpy() for k, v in f.items()}
+    import geocalib_b200 as G
+
+    with torch.no_grad():
+        out = G.LMOptimizer({"camera_model": model, **conf}).eval()(f)
+    torch.cuda.synchronize()
+    ref = oracle.lm(model, fn["up_field"], fn["latitude_field"], fn["up_confidence"], fn["latitude_confidence"],
+                    conf=conf)
+    cam, grav = out["camera"]._data.cpu().numpy(), out["gravity"]._data.cpu().numpy()
+    assert_params_close(cam, grav, ref["camera"], ref["gravity"], model, tol=TOL)
+    assert np.abs(out["stop_at"].cpu().numpy() - ref["stop_at"]).max() <= 1
+    np.testing.assert_allclose(out["final_cost"].cpu().numpy(), ref["final_cost"], rtol=2e-4)
+    # the calibration is also RIGHT (not just equal): focal within 2 % of the synthetic ground truth
+    assert np.median(np.abs(cam[:, 3] / cam_gt[:, 3] - 1)) < 0.02
