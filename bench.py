@@ -190,7 +190,7 @@ def port_run(model, fields, iters, threads):
 
 def port_baseline(model, h, w, iters, target_seconds=12.0):
     """The C/OpenMP port (oracle/gclm_oracle.c) on all host threads; sample sized to ~target_seconds."""
-    cores = host_threads()
+    cores = effective_cpus()
     probe_n = max(8, min(64, cores // 2))
     fields = cpu_sample_fields(model, probe_n, h, w, 99)
     dt = port_run(model, fields, iters, cores)
@@ -205,86 +205,161 @@ def port_baseline(model, h, w, iters, target_seconds=12.0):
                       f"in {dt:.1f} s; oracle/gclm_oracle.c, OpenMP over (image, row-chunk) tasks"}
 
 
-class ReferenceRunner:
-    """The UNMODIFIED reference LMOptimizer (geocalib/lm_optimizer.py:551-664) from baseline/_ref on the
-    host CPU: torch eager, all host threads, chunks of 8 images (4 at >= 1 Mpixel) as BASELINE.md 3 says
-    (it materialises (B,N,2,n) Jacobians).  Inputs: the reference's own get_perspective_field + noise."""
+def effective_cpus():
+    """Host threads this process may really use: the affinity mask capped by the cgroup CPU quota (a
+    container that sees 128 CPUs but owns a fraction of them oversubscribes every thread pool)."""
+    n = host_threads()
+    try:
+        q, p = Path("/sys/fs/cgroup/cpu.max").read_text().split()[:2]
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(p))))
+    except Exception:  # noqa: BLE001
+        try:
+            q = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read_text())
+            p = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+            if q > 0:
+                n = min(n, max(1, q // p))
+        except Exception:  # noqa: BLE001
+            pass
+    return n
 
-    def __init__(self, model, h, w, iters, shared=False):
-        import torch
+
+REF_THREADS_PER_PROC = 8  # torch-eager LM does not scale past ~8 threads (0.9 img/s @ 8 vs 0.02 img/s @ 128 threads)
+_REF = {}
+
+
+def _ref_worker_init(model, h, w, iters, shared, threads, n_img, seed_base, counter):
+    """Runs once in every worker process: import the UNMODIFIED reference, build its optimizer and this
+    worker's resident sample of the workload (rendered with the reference's own get_perspective_field)."""
+    import torch
+
+    torch.set_num_threads(threads)  # also overrides the OMP_NUM_THREADS=1 that torch.distributed.run exports
+    sys.path.insert(0, str(ROOT / "baseline"))
+    import ref_import
+
+    ref_import.import_reference()
+    from geocalib.camera import camera_models
+    from geocalib.gravity import Gravity
+    from geocalib.lm_optimizer import LMOptimizer
+    from geocalib.perspective_fields import get_perspective_field
+
+    with counter.get_lock():
+        wid = counter.value
+        counter.value += 1
+    opt = LMOptimizer({"camera_model": model, "num_steps": iters, "early_stop": False}).eval()
+    opt.shared_intrinsics = shared
+    seed = seed_base + wid
+    cam, grav = gt_params(model, n_img, h, w, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        up, lat = get_perspective_field(camera_models[model](torch.from_numpy(cam)), Gravity(torch.from_numpy(grav)))
+        up = up + 0.02 * torch.randn(up.shape, generator=g)
+        up = (up / up.norm(dim=1, keepdim=True)).contiguous()
+        lat = (lat + 0.02 * torch.randn(lat.shape, generator=g)).contiguous()
+        uc = 0.2 + 0.8 * torch.rand((n_img, h, w), generator=g)
+        lc = 0.2 + 0.8 * torch.rand((n_img, h, w), generator=g)
+    _REF.update(opt=opt, data={"up_field": up, "latitude_field": lat, "up_confidence": uc,
+                               "latitude_confidence": lc}, torch=torch, cam_gt=cam)
+
+
+def _ref_worker_step(n_img):
+    """One pass of the reference LM over the first n_img resident images of this worker; returns
+    (seconds, median relative focal error vs the synthetic ground truth)."""
+    torch = _REF["torch"]
+    t = time.perf_counter()
+    with torch.no_grad():
+        out = _REF["opt"]({k: v[:n_img] for k, v in _REF["data"].items()})
+    dt = time.perf_counter() - t
+    f = out["camera"].f[:, 1].numpy()
+    return dt, float(np.median(np.abs(f / _REF["cam_gt"][:n_img, 3] - 1)))
+
+
+class ReferenceRunner:
+    """The UNMODIFIED reference LMOptimizer (geocalib/lm_optimizer.py:551-664, from baseline/_ref) on the host
+    CPU, all usable host threads: P worker processes x 8 torch threads, every worker running chunks of at
+    most 8 images (4 at >= 1 Mpixel) as BASELINE.md 3 prescribes -- the reference materialises (B,N,2,n)
+    Jacobians, and one torch-eager process does not scale past ~8 threads."""
+
+    def __init__(self, model, h, w, iters, shared=False, max_procs=None):
+        import multiprocessing as mp
+        from concurrent.futures import ProcessPoolExecutor
 
         sys.path.insert(0, str(ROOT / "baseline"))
         import ref_import
 
-        ref_import.import_reference()  # raises when baseline/_ref is not installed
-        from geocalib.camera import camera_models
-        from geocalib.gravity import Gravity
-        from geocalib.lm_optimizer import LMOptimizer
-        from geocalib.perspective_fields import get_perspective_field
-
-        self.torch = torch
-        self.cores = host_threads()
-        torch.set_num_threads(self.cores)  # torch.distributed.run exports OMP_NUM_THREADS=1
+        if not ref_import.available():
+            raise ImportError("baseline/_ref is empty (run baseline/install_ref.sh in the build container)")
+        self.cores = effective_cpus()
+        self.threads = min(REF_THREADS_PER_PROC, self.cores)
+        self.procs = max(1, self.cores // self.threads)
+        if max_procs:
+            self.procs = min(self.procs, max_procs)
         self.model, self.h, self.w, self.iters = model, h, w, iters
         self.chunk = 4 if h * w >= (1 << 20) else 8
-        self.opt = LMOptimizer({"camera_model": model, "num_steps": iters, "early_stop": False}).eval()
-        self.opt.shared_intrinsics = shared
-        self._cm, self._Gravity, self._gpf = camera_models[model], Gravity, get_perspective_field
+        ctx = mp.get_context("spawn")
+        counter = ctx.Value("i", 0)
+        env_omp = os.environ.get("OMP_NUM_THREADS")
+        os.environ["OMP_NUM_THREADS"] = str(self.threads)  # inherited by the workers before torch initialises
+        try:
+            self.pool = ProcessPoolExecutor(self.procs, mp_context=ctx, initializer=_ref_worker_init,
+                                            initargs=(model, h, w, iters, shared, self.threads, self.chunk, 9900, counter))
+            self.per_worker = 1
+            self.step()  # spawn + import + TorchScript / allocator warm-up in every worker (1 image each)
+        finally:
+            if env_omp is None:
+                os.environ.pop("OMP_NUM_THREADS", None)
+            else:
+                os.environ["OMP_NUM_THREADS"] = env_omp
+        import torch
+        self.torch_version = torch.__version__
 
-    def fields(self, n, seed):
-        torch = self.torch
-        cam, grav = gt_params(self.model, n, self.h, self.w, seed)
-        g = torch.Generator().manual_seed(seed + 1)
-        with torch.no_grad():
-            up, lat = self._gpf(self._cm(torch.from_numpy(cam)), self._Gravity(torch.from_numpy(grav)))
-            up = up + 0.02 * torch.randn(up.shape, generator=g)
-            up = up / up.norm(dim=1, keepdim=True)
-            lat = lat + 0.02 * torch.randn(lat.shape, generator=g)
-            uc = 0.2 + 0.8 * torch.rand((n, self.h, self.w), generator=g)
-            lc = 0.2 + 0.8 * torch.rand((n, self.h, self.w), generator=g)
-        return {"up_field": up.contiguous(), "latitude_field": lat.contiguous(), "up_confidence": uc,
-                "latitude_confidence": lc}
-
-    def run(self, data):
-        """One pass over `data` in chunks; returns seconds."""
-        torch = self.torch
-        n = data["up_field"].shape[0]
+    def step(self):
+        """Every worker runs the LM once over `per_worker` of its resident images; returns wall seconds."""
         t = time.perf_counter()
-        with torch.no_grad():
-            for s0 in range(0, n, self.chunk):
-                out = self.opt({k: v[s0:s0 + self.chunk] for k, v in data.items()})
-        self.last = out
+        res = list(self.pool.map(_ref_worker_step, [self.per_worker] * self.procs))
+        self.focal_err = float(np.median([r[1] for r in res]))
         return time.perf_counter() - t
 
-    def describe(self, n):
-        return (f"{n} images of the workload ({self.h}x{self.w} {self.model}, {self.iters} LM iterations, "
-                f"early_stop off) in chunks of {self.chunk}; unmodified geocalib.lm_optimizer.LMOptimizer "
-                f"(baseline/_ref), torch {self.torch.__version__} CPU eager, {self.cores} threads")
+    @property
+    def images_per_step(self):
+        return self.per_worker * self.procs
+
+    def size_step(self, seconds):
+        """Pick per_worker in [1, chunk] so that a step takes about `seconds`."""
+        self.per_worker = 1
+        dt1 = self.step()
+        self.per_worker = int(max(1, min(self.chunk, seconds // max(dt1, 1e-3))))
+        return dt1
+
+    def describe(self):
+        return (f"{self.images_per_step} images of the workload ({self.h}x{self.w} {self.model}, {self.iters} LM "
+                f"iterations, early_stop off) per step: {self.procs} processes x {self.threads} torch threads "
+                f"({self.cores} usable host threads), {self.per_worker} image(s) per process and call; unmodified "
+                f"geocalib.lm_optimizer.LMOptimizer (baseline/_ref), torch {self.torch_version} CPU eager")
+
+    def close(self):
+        self.pool.shutdown(wait=True, cancel_futures=True)
 
 
-def reference_baseline(model, h, w, iters, target_seconds=20.0):
+def reference_baseline(model, h, w, iters, target_seconds=15.0):
     """cpu_baseline leg of the GPU arm (kind "reference"); None when baseline/_ref is not installed."""
     try:
         r = ReferenceRunner(model, h, w, iters)
     except Exception as e:  # noqa: BLE001
         return None, f"{type(e).__name__}: {e}"
-    data = r.fields(r.chunk, 99)
-    r.run(data)  # TorchScript / allocator warm-up
-    dt = r.run(data)
-    n = int(min(64, max(1, round(target_seconds / dt)) * r.chunk))
-    if n > r.chunk:
-        data = r.fields(n, 99)
-        dt = r.run(data)
-    else:
-        n = r.chunk
-    return {"value": n / dt, "unit": "images/sec", "cores": r.cores, "kind": "reference",
-            "sample": r.describe(n) + f"; {dt:.1f} s"}, None
+    try:
+        r.size_step(target_seconds)
+        dt = r.step()
+        return {"value": r.images_per_step / dt, "unit": "images/sec", "cores": r.cores, "kind": "reference",
+                "sample": r.describe() + f"; {dt:.1f} s", "median_focal_error_vs_gt": r.focal_err}, None
+    finally:
+        r.close()
 
 
 def run_reference_arm(args, wl):
-    """--impl reference: the unmodified PyTorch reference on all host threads; rank 0 only.
-    One step = one bounded sample (a few chunks) of the workload, sized so that steps + warmup fit in
-    a few minutes; `config` is the GPU arm's, the sample size is stated in cpu_baseline.sample."""
+    """--impl reference: the unmodified PyTorch reference on all usable host threads; rank 0 only.
+    One step = one bounded sample of the workload (a few images per worker process), sized so that
+    steps + warmup fit in a few minutes; `config` is the GPU arm's, the sample is stated in cpu_baseline."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -292,22 +367,15 @@ def run_reference_arm(args, wl):
     world = args.gpus
     shared = args.workload.startswith("shared")
     budget_s = 150.0 / max(1, args.steps + min(args.warmup, 2))  # wall-clock per step
-    kind, note = "reference", None
+    kind, note, r = "reference", None, None
     try:
         r = ReferenceRunner(model, h, w, iters, shared=shared)
-        data = r.fields(r.chunk, 99)
-        r.run(data)  # TorchScript / allocator warm-up (not a step)
-        probe = r.run(data)
-        per_step = int(max(1, min(8, budget_s // probe)) * r.chunk) if probe < budget_s else max(1, int(r.chunk * budget_s / probe))
-        if per_step < r.chunk:
-            r.chunk = per_step
-        if per_step != data["up_field"].shape[0]:
-            data = r.fields(per_step, 99)
-        step = lambda: r.run(data)
-        cores, sample = r.cores, "each step = " + r.describe(per_step)
+        r.size_step(budget_s)
+        step, per_step = r.step, r.images_per_step
+        cores, sample = r.cores, "each step = " + r.describe()
     except ImportError as e:
         kind, note = "port", f"baseline/_ref not installed ({e}); timing the C/OpenMP port instead"
-        cores = host_threads()
+        cores = effective_cpus()
         n = max(8, min(64, cores // 2))
         fields = cpu_sample_fields(model, n, h, w, 99)
         probe = port_run(model, fields, iters, cores)
@@ -333,6 +401,9 @@ def run_reference_arm(args, wl):
         "e2e": {"value": val, "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "images_per_step": per_step,
     }
+    if r is not None:
+        line["median_focal_error_vs_gt"] = r.focal_err
+        r.close()
     if note:
         line["note"] = note
     print(json.dumps(line))
@@ -377,7 +448,7 @@ def parity_block(model, fields, out, iters, shared, n_img):
     if shared:
         return None  # the shared estimate depends on ALL images of all ranks: covered by tests, not by a slice
     ref = oracle.lm(model, fn["up_field"], fn["latitude_field"], fn["up_confidence"], fn["latitude_confidence"],
-                    conf={"num_steps": iters, "early_stop": False}, num_threads=host_threads())
+                    conf={"num_steps": iters, "early_stop": False}, num_threads=effective_cpus())
     rc, rg = ref["camera"].astype(np.float64), ref["gravity"].astype(np.float64)
     K = oracle.NUM_DIST[model]
     e_f = float(np.max(np.abs(cam[:, 3] - rc[:, 3]) / np.abs(rc[:, 3])))

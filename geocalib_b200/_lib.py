@@ -20,7 +20,7 @@ LIB_PATH = Path(_os.environ["GCLM_LIB"]) if _os.environ.get("GCLM_LIB") else CSR
 
 GCLM_OK = 0
 STOP_BATCH, STOP_PER_IMAGE = 0, 1
-STATUS_CHOLESKY_FAILED, STATUS_COV_SINGULAR, STATUS_NONFINITE = 1, 2, 4
+STATUS_CHOLESKY_FAILED, STATUS_COV_SINGULAR, STATUS_NONFINITE, STATUS_COMM_TIMEOUT = 1, 2, 4, 8
 COMM_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
 

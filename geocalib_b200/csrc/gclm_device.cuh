@@ -12,6 +12,15 @@
 //     residual e = n_perp . up_obs:   J^T W J += w s s^T,   J^T W r += w s e.
 //   * The Huber weight still uses the full 2-vector residual (lm_optimizer.py:291-293).
 //   * sin(asin(clamp(l))) == clamp(l)  (perspective_fields.py:208-209 + lm_optimizer.py:262).
+//   * Scaling symmetry of the radial models: f -> f e^d with k_i -> k_i e^{2 i d} leaves the image
+//     unchanged, hence the log-focal column is   J_f = J_X - sum_i 2 i k_i J_{k_i}   with the
+//     "pinhole-like" column X:  up row  c * gamma,  latitude row  -s_u * guv  (verified symbolically for
+//     simple_radial, radial and simple_divisional against the closed forms of SURVEY Appendix A).  The
+//     streaming loop accumulates the columns [g0 g1 X k..] and finish_sums() maps the reduced system to
+//     [g0 g1 f k..] once per image -- the Bc / A / Q terms never enter the hot loop.
+//   * Huber with the scale folded in: with c2 = |r|^2, i' = rsqrt(max(c2, a^2)) (= 1/(a sqrt(max(chi,1)))),
+//     w' = conf i' (= w / a):  cost conf = c2 w' (2/a - i'),  and J^T W J, J^T W r are accumulated with w'
+//     and multiplied by a once per image (lm_optimizer.py:61-87, 291-313).
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -148,7 +157,20 @@ struct PassConst {
   float T00, T01, T10, T11, T20, T21; // tangent basis (3x2): spherical or (roll,pitch)
   float dsx, dsy;                    // focal direction d = (-u dsx, -v dsy): 1,1 (log) or 1/fx,1/fy
   float k1, k2;
+  int div_any_cold;                  // simple_divisional: some pixel of this image needs the literal masked formulas
 };
+
+// Per-launch constants of the robust loss with the scale folded in (see the header comment).
+struct RobustConst {
+  float up_s2, up_2os, lat_s2, lat_2os, lat_ratio;  // a^2, 2/a for both residuals; a_lat / a_up
+};
+GCLM_HD inline RobustConst make_robust_const(float up_scale, float lat_scale) {
+  RobustConst rc;
+  rc.up_s2 = up_scale * up_scale; rc.up_2os = 2.f / up_scale;
+  rc.lat_s2 = lat_scale * lat_scale; rc.lat_2os = 2.f / lat_scale;
+  rc.lat_ratio = lat_scale / up_scale;
+  return rc;
+}
 
 // ---- gravity helpers: geocalib/misc.py:181-259, geocalib/gravity.py:62-101 ----
 GCLM_HD inline void householder(const float g[3], float hv[3], float& beta) {
@@ -198,6 +220,15 @@ GCLM_HD inline void make_pass_const(const float* cam, const float* g, bool spher
   }
   if (log_focal && !rpf) { pc.dsx = 1.f; pc.dsy = 1.f; }
   else { pc.dsx = pc.inv_fx; pc.dsy = pc.inv_fy; }
+  // simple_divisional: the closed form applies to every pixel unless k1 == 0 (all masked branches fire) or
+  // the root is clamped somewhere: 1 - 4 k1 r^2 < 1e-6 first happens in a corner (r^2 is evaluated exactly as
+  // pixel_accumulate does, and fp32 u*u, fma are monotone in |u|, |v|, so the corner bounds every pixel)
+  {
+    const float ux = fmaxf(fabsf((0.f - pc.cx) * pc.inv_fx), fabsf(((cam[0] - 1.f) - pc.cx) * pc.inv_fx));
+    const float vy = fmaxf(fabsf((0.f - pc.cy) * pc.inv_fy), fabsf(((cam[1] - 1.f) - pc.cy) * pc.inv_fy));
+    const float r2max = fmaf(ux, ux, vy * vy);
+    pc.div_any_cold = (pc.k1 == 0.f || fmaf(-4.f * pc.k1, r2max, 1.f) < 1e-6f) ? 1 : 0;
+  }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -300,35 +331,68 @@ GCLM_HD __forceinline__ void model_scalars(const PassConst& pc, V r2, ModelScala
     const V x = fmaf(-4.f * pc.k1, r2, splat<V>(1.f));
     const V xs = fmaxf(x, 1e-6f);
     const V it = fast_rsqrt(xs), t = xs * it, w = 1.f + t, iw = fast_rcp(w);
-    const V itw2 = it * iw * iw, it2 = it * it;
+    const V g4 = (4.f * it) * iw * iw, it2 = it * it;  // 4 / (t w^2)
     m.s = 2.f * iw;
-    m.phi = (8.f * pc.k1) * itw2; m.A = m.phi;
-    m.Bc = (32.f * pc.k1 * pc.k1) * fmaf(3.f, t, splat<V>(1.f)) * itw2 * it2 * iw;
-    m.sk[0] = 4.f * r2 * itw2;
-    m.psi[0] = 4.f * fmaf(t, 2.f - t, splat<V>(1.f)) * itw2 * it2;
+    m.phi = (2.f * pc.k1) * g4; m.A = m.phi;
+    m.Bc = (8.f * pc.k1 * pc.k1) * fmaf(3.f, t, splat<V>(1.f)) * g4 * it2 * iw;  // general focal direction only
+    m.sk[0] = r2 * g4;
+    m.psi[0] = fmaf(t, 2.f - t, splat<V>(1.f)) * g4 * it2;
     const V su = fast_rcp(fmaf(pc.k1, r2, splat<V>(1.f)));
+    const V su2 = su * su;
     m.su = su;
-    m.Q = (-2.f * pc.k1) * su * su;
-    m.om[0] = -(r2 * su * su);
+    m.Q = (-2.f * pc.k1) * su2;  // general focal direction only
+    m.om[0] = -(r2 * su2);
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // one pixel: residuals, robust weights, Jacobian rows, accumulation
 //   acc layout: [H upper triangle row-major (NH)] [G (NF)] [cost_up] [cost_lat]
-//   GEN_D: general focal direction (non-log focal or the final as_rpf pass)
+//   GEN_D: general focal direction (non-log focal or the final as_rpf pass): columns [g0 g1 f k..].
+//   !GEN_D (the LM passes with log focal): columns [g0 g1 X k..] (see the header comment; for pinhole
+//   X == f), weights w' = w / a_up; finish_sums() turns the reduced sums into the system the solver sees.
 //   flags: runtime presence of the inputs (compile-time true when FULL)
 // ------------------------------------------------------------------------------------------
 struct FieldMask { bool up, lat, up_conf, lat_conf; };
 
+// accumulator update a*b + c: packed by default; -DGCLM_SCALAR_ACC issues it as two scalar FFMA (A/B knob)
+GCLM_HD __forceinline__ float fma_acc(float a, float b, float c) { return ::fmaf(a, b, c); }
+GCLM_HD __forceinline__ f2 fma_acc(f2 a, f2 b, f2 c) {
+#if defined(GCLM_SCALAR_ACC)
+  return f2(::fmaf(a.v.x, b.v.x, c.v.x), ::fmaf(a.v.y, b.v.y, c.v.y));
+#else
+  return fmaf(a, b, c);
+#endif
+}
+
+// Column-invariant terms of a pixel (pair): a warp walks DOWN a strip, so anything that depends on x only
+// can be computed once per strip (-DGCLM_HOIST; costs registers) instead of once per row:
+//   p0x = a - c u,  zx_j = T0j - T2j u  (the up-field gravity rows are alpha zx_j + beta zy_j with the
+//   row-uniform zy_j = T1j - T2j v).
+template <class V>
+struct Col { V u, p0x, zx0, zx1; };
+template <class V>
+GCLM_HD __forceinline__ Col<V> make_col(const PassConst& pc, V u) {
+  Col<V> c;
+  c.u = u;
+  c.p0x = fmaf(-pc.c, u, splat<V>(pc.a));
+  c.zx0 = fmaf(-pc.T20, u, splat<V>(pc.T00));
+  c.zx1 = fmaf(-pc.T21, u, splat<V>(pc.T01));
+  return c;
+}
+
 template <int MODEL, bool GEN_D, bool FULL, class V, bool LIT = false, bool K0 = false>
-GCLM_HD __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMask fm, V u,
+GCLM_HD __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMask fm, const Col<V>& col,
                                                  float v, V ox, V oy, V sin_olat, V cu,
-                                                 V cl, float inv_up2, float inv_lat2,
+                                                 V cl, const RobustConst& rc,
                                                  V (&acc)[Dims<MODEL>::NACC]) {
+  const V u = col.u;
   constexpr int K = Dims<MODEL>::K, NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH;
+  // the masked / literal divisional formulas do not obey the scaling symmetry: their focal row is computed
+  // directly and (LIT, k1 != 0) moved into the X basis; K0 means k1 == 0, where X == f
+  constexpr bool DIRECT_F = GEN_D || K0 || LIT;
   const bool has_up = FULL || fm.up, has_lat = FULL || fm.lat;
-  const V r2 = fmaf(u, u, splat<V>(v * v));
+  const V r2 = (u * u) + splat<V>(v * v);  // u*u is column-invariant: the compiler hoists it out of the row loop
   ModelScalars<K, V> m;
   model_scalars<MODEL, V, LIT, K0>(pc, r2, m);
 
@@ -339,11 +403,12 @@ GCLM_HD __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMa
   if constexpr (GEN_D) { dx = -(u * pc.dsx); dy = -v * pc.dsy; uvd = fmaf(u, dx, splat<V>(v * dy)); }
 
   if (has_up) {  // ---- up field: perspective_fields.py:47-182 ----
-    const V p0x = fmaf(-pc.c, u, splat<V>(pc.a));
+    const V p0x = col.p0x;
     const float p0y = fmaf(-pc.c, v, pc.b);
+    const float zy0 = fmaf(-pc.T20, v, pc.T10), zy1 = fmaf(-pc.T21, v, pc.T11);  // row-uniform
     V px = p0x, py = splat<V>(p0y), iota = splat<V>(0.f);
     if constexpr (K > 0) {
-      iota = fmaf(u, p0x, splat<V>(v * p0y));
+      iota = (u * p0x) + splat<V>(v * p0y);  // column-invariant + row-uniform
       const V pi = m.phi * iota;
       px = fmaf(m.s, p0x, pi * u);
       py = fmaf(m.s, splat<V>(p0y), pi * v);
@@ -351,25 +416,22 @@ GCLM_HD __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMa
     const V rho2 = fmaf(px, px, py * py);
     const V irho = fast_rsqrt(fmaxf(rho2, 1e-24f));  // F.normalize eps (perspective_fields.py:79)
     const V upx = px * irho, upy = py * irho;
-    const V q = irho * irho;
-    const V Ap = -(py * q), Bp = px * q;  // (n_perp . z)/rho = Ap z_x + Bp z_y
+    const V Ap = -(upy * irho), Bp = upx * irho;  // (n_perp . z)/rho = Ap z_x + Bp z_y
     const V Nu = fmaf(Ap, u, Bp * v);
     // residual (lm_optimizer.py:266) and its component along n_perp
     const V rx = ox - upx, ry = oy - upy;
     e = fmaf(upx, oy, -(upy * ox));
-    const V chi = fmaf(rx, rx, ry * ry) * inv_up2;
-    // Huber (lm_optimizer.py:79-87): chi + 1e-8 == chi in fp32 for chi > 1
-    const V mm = fmaxf(chi, 1.f);
-    const V isx = fast_rsqrt(mm);
-    // cost*conf = min(chi,1) (2 sqrt(max(chi,1)) - 1) conf = 2 chi w - min(chi,1) conf, w = conf/sqrt(max(chi,1))
+    // Huber (lm_optimizer.py:79-87; chi + 1e-8 == chi in fp32 for chi > 1), scale folded in
+    const V c2 = fmaf(rx, rx, ry * ry);
+    const V isx = fast_rsqrt(fmaxf(c2, rc.up_s2));
     w_up = isx * cu;
-    acc[NH + NF] = fmaf(chi + chi, w_up, fmaf(-fminf(chi, 1.f), cu, acc[NH + NF]));
+    acc[NH + NF] = fmaf(c2 * w_up, rc.up_2os - isx, acc[NH + NF]);
     // Jacobian columns.  With M z = s z + phi uv (uv.z) and z_j = (T0j - u T2j, T1j - v T2j):
     //   s_j = T0j alpha + T1j beta - T2j gamma,  alpha = s Ap + phi Nu u, beta = s Bp + phi Nu v,
     //   gamma = alpha u + beta v = Nu (s + phi r^2)        (Nu = Ap u + Bp v)
     if constexpr (K == 0) {
-      su_[0] = fmaf(Ap, pc.T00, fmaf(Bp, pc.T10, -pc.T20 * Nu));
-      su_[1] = fmaf(Ap, pc.T01, fmaf(Bp, pc.T11, -pc.T21 * Nu));
+      su_[0] = fmaf(Ap, col.zx0, Bp * zy0);
+      su_[1] = fmaf(Ap, col.zx1, Bp * zy1);
       if constexpr (!GEN_D) su_[2] = pc.c * Nu;
       else su_[2] = -pc.c * fmaf(Ap, dx, Bp * dy);
     } else {
@@ -377,29 +439,30 @@ GCLM_HD __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMa
       const V alpha = fmaf(pn, u, m.s * Ap), beta = fmaf(pn, v, m.s * Bp);
       const V pr2 = m.phi * r2;
       const V gamma = Nu * (m.s + pr2);
-      su_[0] = fmaf(alpha, pc.T00, fmaf(beta, pc.T10, -pc.T20 * gamma));
-      su_[1] = fmaf(alpha, pc.T01, fmaf(beta, pc.T11, -pc.T21 * gamma));
+      su_[0] = fmaf(alpha, col.zx0, beta * zy0);
+      su_[1] = fmaf(alpha, col.zx1, beta * zy1);
       const V Np0 = fmaf(Ap, p0x, Bp * p0y);  // (n_perp . p0)/rho
       const V iN = iota * Nu;
-      if constexpr (!GEN_D) {
+#pragma unroll
+      for (int k = 0; k < K; k++) su_[3 + k] = fmaf(m.sk[k], Np0, m.psi[k] * iN);
+      if constexpr (!DIRECT_F) {
+        su_[2] = pc.c * gamma;  // column X
+      } else if constexpr (!GEN_D) {
         // log-focal column (d = -uv): c gamma - iota Nu (Bc r^2 + A + phi) - phi r^2 Np0
-        V t;
-        if constexpr (MODEL == SIMPLE_RADIAL) t = (4.f * pc.k1) * iN;  // Bc = 0, A = phi = 2 k1
-        else t = iN * (fmaf(m.Bc, r2, m.A) + m.phi);
+        const V t = iN * (fmaf(m.Bc, r2, m.A) + m.phi);
         su_[2] = fmaf(-pr2, Np0, fmaf(pc.c, gamma, -t));
+        if constexpr (LIT) su_[2] = fmaf(2.f * pc.k1, su_[3], su_[2]);  // X = f + 2 k1 k (one-parameter model)
       } else {
         const V Nd = fmaf(Ap, dx, Bp * dy);
         const V p0d = fmaf(p0x, dx, splat<V>(p0y * dy));
         const V t = fmaf(iota * m.Bc, uvd, m.phi * (p0d - pc.c * uvd));
         su_[2] = fmaf(fmaf(iota, m.A, -pc.c * m.s), Nd, fmaf(m.phi * uvd, Np0, Nu * t));
       }
-#pragma unroll
-      for (int k = 0; k < K; k++) su_[3 + k] = fmaf(m.sk[k], Np0, m.psi[k] * iN);
     }
   }
 
   if (has_lat) {  // ---- latitude field: perspective_fields.py:185-275 ----
-    const V S = fmaf(pc.a, u, splat<V>(pc.b * v));
+    const V S = (pc.a * u) + splat<V>(pc.b * v);  // column-invariant + row-uniform
     V m2, ln;
     if constexpr (K == 0) { m2 = r2 + 1.f; ln = S + pc.c; }
     else { m2 = fmaf(m.su * m.su, r2, splat<V>(1.f)); ln = fmaf(m.su, S, splat<V>(pc.c)); }
@@ -407,17 +470,17 @@ GCLM_HD __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMa
     const V l = ln * im;
     const V lc = fminf(fmaxf(l, -1.f + 1e-6f), 1.f - 1e-6f);
     r_lat = sin_olat - lc;  // lm_optimizer.py:270-271
-    const V chi = r_lat * r_lat * inv_lat2;
-    const V mm = fmaxf(chi, 1.f);
-    const V isx = fast_rsqrt(mm);
+    const V c2 = r_lat * r_lat;
+    const V isx = fast_rsqrt(fmaxf(c2, rc.lat_s2));
     w_lat = isx * cl;
-    acc[NH + NF + 1] = fmaf(chi + chi, w_lat, fmaf(-fminf(chi, 1.f), cl, acc[NH + NF + 1]));
+    acc[NH + NF + 1] = fmaf(c2 * w_lat, rc.lat_2os - isx, acc[NH + NF + 1]);
+    if (rc.lat_ratio != 1.f) w_lat = w_lat * rc.lat_ratio;  // both residuals share the a_up of finish_sums
     if constexpr (K == 0) {
-      sl_[0] = im * fmaf(pc.T00, u, splat<V>(fmaf(pc.T10, v, pc.T20)));
-      sl_[1] = im * fmaf(pc.T01, u, splat<V>(fmaf(pc.T11, v, pc.T21)));
+      sl_[0] = im * ((pc.T00 * u) + splat<V>(fmaf(pc.T10, v, pc.T20)));
+      sl_[1] = im * ((pc.T01 * u) + splat<V>(fmaf(pc.T11, v, pc.T21)));
     } else {
-      sl_[0] = im * fmaf(m.su, fmaf(pc.T00, u, splat<V>(pc.T10 * v)), splat<V>(pc.T20));
-      sl_[1] = im * fmaf(m.su, fmaf(pc.T01, u, splat<V>(pc.T11 * v)), splat<V>(pc.T21));
+      sl_[0] = im * fmaf(m.su, (pc.T00 * u) + splat<V>(pc.T10 * v), splat<V>(pc.T20));
+      sl_[1] = im * fmaf(m.su, (pc.T01 * u) + splat<V>(pc.T11 * v), splat<V>(pc.T21));
     }
     const V li = l * im;
     if constexpr (!GEN_D) {
@@ -425,9 +488,14 @@ GCLM_HD __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMa
         sl_[2] = im * fmaf(-l, im, splat<V>(pc.c));  // = -gamma.uv with r^2 = m^2 - 1
       } else {
         const V guv = im * fmaf(-(li * m.su), r2, S);
-        sl_[2] = -(fmaf(m.Q, r2, m.su) * guv);
 #pragma unroll
         for (int k = 0; k < K; k++) sl_[3 + k] = m.om[k] * guv;
+        if constexpr (!DIRECT_F) {
+          sl_[2] = -(m.su * guv);  // column X
+        } else {
+          sl_[2] = -(fmaf(m.Q, r2, m.su) * guv);
+          if constexpr (LIT) sl_[2] = fmaf(2.f * pc.k1, sl_[3], sl_[2]);
+        }
       }
     } else {
       const V U = m.su * u, Vv = m.su * v;
@@ -455,18 +523,56 @@ GCLM_HD __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMa
 #pragma unroll
     for (int j = i; j < NF; j++) {
       V h = acc[idx];
-      if (has_up) h = fmaf(wu[i], su_[j], h);
-      if (has_lat) h = fmaf(wl[i], sl_[j], h);
+      if (has_up) h = fma_acc(wu[i], su_[j], h);
+      if (has_lat) h = fma_acc(wl[i], sl_[j], h);
       acc[idx++] = h;
     }
   }
 #pragma unroll
   for (int i = 0; i < NF; i++) {
     V g = acc[NH + i];
-    if (has_up) g = fmaf(wu[i], e, g);
-    if (has_lat) g = fmaf(wl[i], r_lat, g);
+    if (has_up) g = fma_acc(wu[i], e, g);
+    if (has_lat) g = fma_acc(wl[i], r_lat, g);
     acc[NH + i] = g;
   }
+}
+
+// Reduced sums of one image -> the system the solver sees: undo the folded robust scale (x a_up) and, for
+// the LM passes of the distortion models (!GEN_D), map the columns [g0 g1 X k..] to [g0 g1 f k..]:
+//   J_f = J_X + sum_i kappa_i J_{k_i},  kappa_i = -2 i k_i.   T = float (kernel) or double (host test).
+template <int MODEL, bool GEN_D, class T>
+GCLM_HD inline void finish_sums(T* s, float k1, float k2, float up_scale) {
+  constexpr int K = Dims<MODEL>::K, NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH;
+  if constexpr (K > 0 && !GEN_D) {
+    const T kap[2] = {(T)(-2.f * k1), (T)(-4.f * k2)};
+    T Hf[NF][NF];
+    {
+      int idx = 0;
+      for (int i = 0; i < NF; i++)
+        for (int j = i; j < NF; j++) { Hf[i][j] = s[idx]; Hf[j][i] = s[idx]; idx++; }
+    }
+    // column/row 2: f = X + sum kappa_i k_i
+    T hff = Hf[2][2];
+    for (int i = 0; i < K; i++) {
+      hff += (T)2 * kap[i] * Hf[2][3 + i];
+      for (int j = 0; j < K; j++) hff += kap[i] * kap[j] * Hf[3 + i][3 + j];
+    }
+    T col[NF];
+    for (int r = 0; r < NF; r++) {
+      T c = Hf[r][2];
+      for (int i = 0; i < K; i++) c += kap[i] * Hf[r][3 + i];
+      col[r] = c;
+    }
+    for (int r = 0; r < NF; r++) { Hf[r][2] = col[r]; Hf[2][r] = col[r]; }
+    Hf[2][2] = hff;
+    T gf = s[NH + 2];
+    for (int i = 0; i < K; i++) gf += kap[i] * s[NH + 3 + i];
+    s[NH + 2] = gf;
+    int idx = 0;
+    for (int i = 0; i < NF; i++)
+      for (int j = i; j < NF; j++) s[idx++] = Hf[i][j];
+  }
+  for (int i = 0; i < NH + NF; i++) s[i] *= (T)up_scale;
 }
 
 // simple_divisional: does pixel (u, v) need the literal masked formulas?  k1 == 0 (trivial init:
@@ -479,12 +585,12 @@ GCLM_HD __forceinline__ bool divisional_is_cold(const PassConst& pc, float u, fl
 // their address taken.
 template <int MODEL, bool GEN_D, bool FULL, bool LIT>
 GCLM_HD __noinline__ void pixel_scalar(const PassConst& pc, const FieldMask fm, float u, float v, float ox,
-                                           float oy, float sin_olat, float cu, float cl, float inv_up2,
-                                           float inv_lat2, float* d) {
+                                           float oy, float sin_olat, float cu, float cl, const RobustConst& rc,
+                                           float* d) {
   float a1[Dims<MODEL>::NACC];
 #pragma unroll
   for (int i = 0; i < Dims<MODEL>::NACC; i++) a1[i] = 0.f;
-  pixel_accumulate<MODEL, GEN_D, FULL, float, LIT>(pc, fm, u, v, ox, oy, sin_olat, cu, cl, inv_up2, inv_lat2, a1);
+  pixel_accumulate<MODEL, GEN_D, FULL, float, LIT>(pc, fm, make_col<float>(pc, u), v, ox, oy, sin_olat, cu, cl, rc, a1);
 #pragma unroll
   for (int i = 0; i < Dims<MODEL>::NACC; i++) d[i] = a1[i];
 }
@@ -495,55 +601,81 @@ GCLM_HD __forceinline__ float pixel_v(const PassConst& pc, int y) { return ((flo
 
 // Four consecutive pixels of one image row (one float4 of every plane; `ol` = sin(latitude)) into the
 // accumulators: the body of lm_pass_kernel's streaming loop, also run on the host by tests/host_math.
+// The column terms of the four consecutive pixels a lane owns (two pairs when packed).
+template <bool PACK>
+struct RowCols {
+  using V = typename std::conditional<PACK, f2, float>::type;
+  Col<V> c[PACK ? 2 : 4];
+  float u[4];
+};
+template <bool PACK>
+GCLM_HD __forceinline__ RowCols<PACK> make_row_cols(const PassConst& pc, const float (&u)[4]) {
+  RowCols<PACK> r;
+#pragma unroll
+  for (int i = 0; i < 4; i++) r.u[i] = u[i];
+  if constexpr (PACK) {
+    r.c[0] = make_col<f2>(pc, f2(u[0], u[1]));
+    r.c[1] = make_col<f2>(pc, f2(u[2], u[3]));
+  } else {
+#pragma unroll
+    for (int i = 0; i < 4; i++) r.c[i] = make_col<float>(pc, u[i]);
+  }
+  return r;
+}
+
 template <int MODEL, bool GEN_D, bool FULL, bool PACK>
-GCLM_HD __forceinline__ void row_accumulate(const PassConst& pc, const FieldMask fm, const float (&u)[4], float v,
+GCLM_HD __forceinline__ void row_accumulate(const PassConst& pc, const FieldMask fm, const RowCols<PACK>& cols, float v,
                                             const float4 ox, const float4 oy, const float4 ol, const float4 cu,
-                                            const float4 cl, float inv_up2, float inv_lat2,
+                                            const float4 cl, const RobustConst& rc,
                                             typename std::conditional<PACK, f2, float>::type (&acc)[Dims<MODEL>::NACC]) {
   constexpr int NACC = Dims<MODEL>::NACC;
   using V = typename std::conditional<PACK, f2, float>::type;
   const float sl0 = ol.x, sl1 = ol.y, sl2 = ol.z, sl3 = ol.w;
-  if constexpr (MODEL == SIMPLE_DIVISIONAL && PACK) {
-    if (pc.k1 == 0.f) {  // whole image (first pass from the trivial init, zero prior): packed k1 == 0 form
-      pixel_accumulate<MODEL, GEN_D, FULL, f2, false, true>(pc, fm, f2(u[0], u[1]), v, f2(ox.x, ox.y), f2(oy.x, oy.y),
-                                                            f2(sl0, sl1), f2(cu.x, cu.y), f2(cl.x, cl.y), inv_up2, inv_lat2, acc);
-      pixel_accumulate<MODEL, GEN_D, FULL, f2, false, true>(pc, fm, f2(u[2], u[3]), v, f2(ox.z, ox.w), f2(oy.z, oy.w),
-                                                            f2(sl2, sl3), f2(cu.z, cu.w), f2(cl.z, cl.w), inv_up2, inv_lat2, acc);
-      return;
-    }
-  }
+  const float (&u)[4] = cols.u;
   if constexpr (MODEL == SIMPLE_DIVISIONAL) {
-    // rare pixels (clamped square root; with scalar math also the k1 == 0 passes) go through the
-    // literal masked formulas, one at a time
-    const bool c0 = divisional_is_cold(pc, u[0], v), c1 = divisional_is_cold(pc, u[1], v);
-    const bool c2 = divisional_is_cold(pc, u[2], v), c3 = divisional_is_cold(pc, u[3], v);
-    if (c0 | c1 | c2 | c3) {
-      float d[NACC];
-      const float us[4] = {u[0], u[1], u[2], u[3]};
-      const float oxs[4] = {ox.x, ox.y, ox.z, ox.w}, oys[4] = {oy.x, oy.y, oy.z, oy.w};
-      const float sls[4] = {sl0, sl1, sl2, sl3}, cus[4] = {cu.x, cu.y, cu.z, cu.w}, cls[4] = {cl.x, cl.y, cl.z, cl.w};
-      const bool cold[4] = {c0, c1, c2, c3};
-      constexpr float share = is_f2<V>::value ? 0.5f : 1.f;  // packed: both halves of an accumulator sum to d
-#pragma unroll 1
-      for (int i = 0; i < 4; i++) {
-        if (cold[i]) pixel_scalar<MODEL, GEN_D, FULL, true>(pc, fm, us[i], v, oxs[i], oys[i], sls[i], cus[i], cls[i], inv_up2, inv_lat2, d);
-        else pixel_scalar<MODEL, GEN_D, FULL, false>(pc, fm, us[i], v, oxs[i], oys[i], sls[i], cus[i], cls[i], inv_up2, inv_lat2, d);
-#pragma unroll
-        for (int k = 0; k < NACC; k++) acc[k] = acc[k] + splat<V>(share * d[k]);
+    if (pc.div_any_cold) {  // uniform per image: k1 == 0 or a clamped square root somewhere in the image
+      if constexpr (PACK) {
+        if (pc.k1 == 0.f) {  // whole image (first pass from the trivial init, zero prior): packed k1 == 0 form
+          pixel_accumulate<MODEL, GEN_D, FULL, f2, false, true>(pc, fm, cols.c[0], v, f2(ox.x, ox.y), f2(oy.x, oy.y),
+                                                                f2(sl0, sl1), f2(cu.x, cu.y), f2(cl.x, cl.y), rc, acc);
+          pixel_accumulate<MODEL, GEN_D, FULL, f2, false, true>(pc, fm, cols.c[1], v, f2(ox.z, ox.w), f2(oy.z, oy.w),
+                                                                f2(sl2, sl3), f2(cu.z, cu.w), f2(cl.z, cl.w), rc, acc);
+          return;
+        }
       }
-      return;
+      // rare pixels (clamped square root; with scalar math also the k1 == 0 passes) go through the
+      // literal masked formulas, one at a time
+      const bool c0 = divisional_is_cold(pc, u[0], v), c1 = divisional_is_cold(pc, u[1], v);
+      const bool c2 = divisional_is_cold(pc, u[2], v), c3 = divisional_is_cold(pc, u[3], v);
+      if (c0 | c1 | c2 | c3) {
+        float d[NACC];
+        const float us[4] = {u[0], u[1], u[2], u[3]};
+        const float oxs[4] = {ox.x, ox.y, ox.z, ox.w}, oys[4] = {oy.x, oy.y, oy.z, oy.w};
+        const float sls[4] = {sl0, sl1, sl2, sl3}, cus[4] = {cu.x, cu.y, cu.z, cu.w}, cls[4] = {cl.x, cl.y, cl.z, cl.w};
+        const bool cold[4] = {c0, c1, c2, c3};
+        constexpr float share = is_f2<V>::value ? 0.5f : 1.f;  // packed: both halves of an accumulator sum to d
+#pragma unroll 1
+        for (int i = 0; i < 4; i++) {
+          // the k1 == 0 literal path yields the f column directly; X == f there (kappa = 0)
+          if (cold[i]) pixel_scalar<MODEL, GEN_D, FULL, true>(pc, fm, us[i], v, oxs[i], oys[i], sls[i], cus[i], cls[i], rc, d);
+          else pixel_scalar<MODEL, GEN_D, FULL, false>(pc, fm, us[i], v, oxs[i], oys[i], sls[i], cus[i], cls[i], rc, d);
+#pragma unroll
+          for (int k = 0; k < NACC; k++) acc[k] = acc[k] + splat<V>(share * d[k]);
+        }
+        return;
+      }
     }
   }
   if constexpr (PACK) {
-    pixel_accumulate<MODEL, GEN_D, FULL, f2>(pc, fm, f2(u[0], u[1]), v, f2(ox.x, ox.y), f2(oy.x, oy.y),
-                                             f2(sl0, sl1), f2(cu.x, cu.y), f2(cl.x, cl.y), inv_up2, inv_lat2, acc);
-    pixel_accumulate<MODEL, GEN_D, FULL, f2>(pc, fm, f2(u[2], u[3]), v, f2(ox.z, ox.w), f2(oy.z, oy.w),
-                                             f2(sl2, sl3), f2(cu.z, cu.w), f2(cl.z, cl.w), inv_up2, inv_lat2, acc);
+    pixel_accumulate<MODEL, GEN_D, FULL, f2>(pc, fm, cols.c[0], v, f2(ox.x, ox.y), f2(oy.x, oy.y),
+                                             f2(sl0, sl1), f2(cu.x, cu.y), f2(cl.x, cl.y), rc, acc);
+    pixel_accumulate<MODEL, GEN_D, FULL, f2>(pc, fm, cols.c[1], v, f2(ox.z, ox.w), f2(oy.z, oy.w),
+                                             f2(sl2, sl3), f2(cu.z, cu.w), f2(cl.z, cl.w), rc, acc);
   } else {
-    pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[0], v, ox.x, oy.x, sl0, cu.x, cl.x, inv_up2, inv_lat2, acc);
-    pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[1], v, ox.y, oy.y, sl1, cu.y, cl.y, inv_up2, inv_lat2, acc);
-    pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[2], v, ox.z, oy.z, sl2, cu.z, cl.z, inv_up2, inv_lat2, acc);
-    pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, u[3], v, ox.w, oy.w, sl3, cu.w, cl.w, inv_up2, inv_lat2, acc);
+    pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, cols.c[0], v, ox.x, oy.x, sl0, cu.x, cl.x, rc, acc);
+    pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, cols.c[1], v, ox.y, oy.y, sl1, cu.y, cl.y, rc, acc);
+    pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, cols.c[2], v, ox.z, oy.z, sl2, cu.z, cl.z, rc, acc);
+    pixel_accumulate<MODEL, GEN_D, FULL, float>(pc, fm, cols.c[3], v, ox.w, oy.w, sl3, cu.w, cl.w, rc, acc);
   }
 }
 

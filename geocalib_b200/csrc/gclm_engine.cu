@@ -54,6 +54,24 @@ struct Ctrl {
   int stop_at;         // first iteration (1-based) at which all images were converged
   unsigned done[2];    // images finished in the current pass (ping-pong by pass parity)
   unsigned unconv[2];  // images NOT converged in the current pass
+  unsigned img_done;   // shared intrinsics: images whose Schur partials of this pass are written
+  int comm_error;      // sticky: a peer's contribution never arrived (fused exchange timed out)
+};
+
+// One-shot all-reduce over NVLink peer memory, fused into the pass kernel's epilogue: every rank stores its
+// 25 partial sums straight into a slot of EVERY peer's exchange buffer (P2P stores through the
+// NVSwitch), publishes a sequence number with system-scope release semantics, waits until all
+// peers' sequence numbers have arrived in its own buffer and adds the contributions in rank order
+// (bit-identical on every rank).  Two slots (seq & 1): a rank can never be two exchanges ahead.
+constexpr int P2P_MAX_RANKS = 8;
+struct P2PBuf {  // one per rank, mapped into every peer with CUDA IPC
+  float data[2][P2P_MAX_RANKS][32];
+  unsigned flag[2][P2P_MAX_RANKS];
+};
+struct P2PArgs {
+  P2PBuf* peer[P2P_MAX_RANKS];  // peer[r] = rank r's buffer as seen from this device (peer[rank] = local)
+  int world, rank;
+  unsigned seq;  // > 0, identical on all ranks for this exchange; world == 0 disables the exchange
 };
 
 struct PassArgs {
@@ -80,6 +98,11 @@ struct PassArgs {
   float* schur;        // (B,SCHUR_STRIDE)
   gclm_result res;
   // gclm_system (diagnostic): raw J^T W r / J^T W J / mean costs of the single pass, full columns
+  // shared intrinsics: 1 = the last CTA of the pass reduces the Schur partials, exchanges them with the peers
+  // (pp) and applies the update; 0 = separate kernels around an NCCL all-reduce (fallback)
+  int fused_shared;
+  float* shared_sums;  // (SCHUR_NSUM + 1) all-reduced sums of the current step
+  P2PArgs pp;
   int final_rpf;       // basis of the final pass: 1 = (roll,pitch) + linear focal (covariance), 0 = LM basis
   float *sys_g, *sys_h, *sys_cost;
 };
@@ -403,22 +426,6 @@ __device__ __noinline__ void schur_image(const PassArgs& a, int b, const float* 
   out[31] = wg[0]; out[32] = wg[1];
 }
 
-// One-shot all-reduce over NVLink peer memory, fused into the reduction kernel: every rank stores its
-// 25 partial sums straight into a slot of EVERY peer's exchange buffer (P2P stores through the
-// NVSwitch), publishes a sequence number with system-scope release semantics, waits until all
-// peers' sequence numbers have arrived in its own buffer and adds the contributions in rank order
-// (bit-identical on every rank).  Two slots (seq & 1): a rank can never be two exchanges ahead.
-constexpr int P2P_MAX_RANKS = 8;
-struct P2PBuf {  // one per rank, mapped into every peer with CUDA IPC
-  float data[2][P2P_MAX_RANKS][32];
-  unsigned flag[2][P2P_MAX_RANKS];
-};
-struct P2PArgs {
-  P2PBuf* peer[P2P_MAX_RANKS];  // peer[r] = rank r's buffer as seen from this device (peer[rank] = local)
-  int world, rank;
-  unsigned seq;  // > 0, identical on all ranks for this exchange; world == 0 disables the exchange
-};
-
 __device__ __forceinline__ void st_release_sys(unsigned* p, unsigned v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -428,26 +435,45 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned* p) {
   return v;
 }
 
-// Sum the per-image Schur partials of this rank in a fixed order -> sum_out[SCHUR_NSUM].
-__global__ void __launch_bounds__(1024) shared_reduce_kernel(const __grid_constant__ PassArgs a, float* sum_out,
-                                                            const __grid_constant__ P2PArgs pp) {
-  __shared__ float s[32][SCHUR_NSUM];
-  if (*(volatile int*)&a.ctrl->stop) return;
-  const int j = threadIdx.x & 31, grp = threadIdx.x >> 5;
-  if (j < SCHUR_NSUM) {
-    float acc = 0.f;
-    for (int b = grp; b < a.B; b += 32) acc += a.schur[(size_t)b * SCHUR_STRIDE + j];
-    s[grp][j] = acc;
+// Sum of this rank's per-image Schur partials, in an order that depends on the block size only: thread t
+// adds images t, t + nthreads, ... (independent 128-bit loads), a warp shuffle tree, then the warps in
+// order.  Block-wide call; the result is valid in threads j < SCHUR_NSUM.
+__device__ __forceinline__ float schur_block_sum(const PassArgs& a, float (*s_part)[SCHUR_NSUM + 3]) {
+  float acc[SCHUR_NSUM + 3];
+#pragma unroll
+  for (int j = 0; j < SCHUR_NSUM + 3; j++) acc[j] = 0.f;
+  for (int b = threadIdx.x; b < a.B; b += blockDim.x) {
+    const float4* p = reinterpret_cast<const float4*>(a.schur + (size_t)b * SCHUR_STRIDE);
+#pragma unroll
+    for (int q = 0; q < (SCHUR_NSUM + 3) / 4; q++) {
+      const float4 x = __ldcg(p + q);
+      acc[4 * q] += x.x; acc[4 * q + 1] += x.y; acc[4 * q + 2] += x.z; acc[4 * q + 3] += x.w;
+    }
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+#pragma unroll
+  for (int j = 0; j < SCHUR_NSUM; j++) {
+    float x = acc[j];
+    x += __shfl_xor_sync(0xffffffffu, x, 16);
+    x += __shfl_xor_sync(0xffffffffu, x, 8);
+    x += __shfl_xor_sync(0xffffffffu, x, 4);
+    x += __shfl_xor_sync(0xffffffffu, x, 2);
+    x += __shfl_xor_sync(0xffffffffu, x, 1);
+    if (lane == 0) s_part[warp][j] = x;
   }
   __syncthreads();
   float mine = 0.f;
-  if (threadIdx.x < SCHUR_NSUM) {
-    for (int g = 0; g < 32; g++) mine += s[g][threadIdx.x];
-    if (pp.world <= 1) sum_out[threadIdx.x] = mine;
-  }
-  if (pp.world <= 1) return;
-  // ---- exchange (warp 0 only) ----
-  if (threadIdx.x >= 32) return;
+  if (threadIdx.x < SCHUR_NSUM)
+    for (int w = 0; w < nwarps; w++) mine += s_part[w][threadIdx.x];
+  return mine;
+}
+
+// Exchange of the SCHUR_NSUM sums with the peers (see P2PBuf); executed by warp 0, `mine` valid in lanes
+// j < SCHUR_NSUM.  Returns the total over ranks in those lanes.  A peer that never shows up (bounded wait,
+// ~1 minute) latches ctrl->comm_error and ctrl->stop on THIS rank: its solve ends flagged, it stops
+// contributing, and the peers run into the same time-out one step later -- no rank keeps iterating alone.
+__device__ __forceinline__ float p2p_exchange(const PassArgs& a, float mine) {
+  const P2PArgs& pp = a.pp;
   const int slot = pp.seq & 1u;
   if (threadIdx.x < SCHUR_NSUM)
     for (int r = 0; r < pp.world; r++) pp.peer[r]->data[slot][pp.rank][threadIdx.x] = mine;  // P2P stores
@@ -459,25 +485,25 @@ __global__ void __launch_bounds__(1024) shared_reduce_kernel(const __grid_consta
     const unsigned* f = &pp.peer[pp.rank]->flag[slot][threadIdx.x];
     unsigned spins = 0;
     while (ld_acquire_sys(f) != pp.seq) {
-      if (++spins > (1u << 27)) { ok = false; break; }
-      __nanosleep(64);
+      if (++spins > (1u << 28)) { ok = false; break; }
+      __nanosleep(spins < 4096u ? 32 : 256);
     }
   }
   ok = __all_sync(0xffffffffu, ok);
+  float tot = 0.f;
   if (threadIdx.x < SCHUR_NSUM) {
-    float acc = 0.f;
     const P2PBuf* me = pp.peer[pp.rank];
-    for (int r = 0; r < pp.world; r++) acc += *(volatile const float*)&me->data[slot][r][threadIdx.x];
-    sum_out[threadIdx.x] = ok ? acc : __int_as_float(0x7fc00000);  // a lost peer poisons the step, never hangs
+    for (int r = 0; r < pp.world; r++) tot += *(volatile const float*)&me->data[slot][r][threadIdx.x];
+    if (!ok) tot = __int_as_float(0x7fc00000);
   }
+  if (!ok && threadIdx.x == 0) { a.ctrl->comm_error = 1; a.ctrl->stop = 1; }
+  return tot;
 }
 
-// Every image redundantly solves the tiny Schur system and applies its own update.
+// One image: solve the (tiny, identical on every image and rank) Schur system and apply the update.
 template <int MODEL>
-__global__ void shared_update_kernel(const __grid_constant__ PassArgs a, const float* sum_in) {
+__device__ __forceinline__ void shared_update_image(const PassArgs& a, int b, const float* sum_in) {
   constexpr int K = Dims<MODEL>::K;
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (*(volatile int*)&a.ctrl->stop) return;
   const int ng = a.est_gravity ? 2 : 0;
   const int ni = (a.est_focal ? 1 : 0) + K;
   float S[9], rhs[3];
@@ -494,40 +520,73 @@ __global__ void shared_update_kernel(const __grid_constant__ PassArgs a, const f
     if (ok) cholesky_solve(S, ni, rhs);
   }
   if (!ok) for (int i = 0; i < 3; i++) rhs[i] = 0.f;  // zero step for everybody (:129-133)
-  const bool all_converged = a.pass >= 1 && sum_in[24] == 0.f;
-  if (b == 0 && all_converged) {
-    if (a.pass < a.ctrl->stop_at) a.ctrl->stop_at = a.pass;
+  const float* sc = a.schur + (size_t)b * SCHUR_STRIDE;
+  float d0 = 0.f, d1 = 0.f;
+  if (ng == 2 && ok) {
+    d0 = sc[31]; d1 = sc[32];
+    for (int j = 0; j < ni; j++) { d0 -= sc[25 + j] * rhs[j]; d1 -= sc[28 + j] * rhs[j]; }
   }
-  if (b < a.B) {
-    const float* sc = a.schur + (size_t)b * SCHUR_STRIDE;
-    float d0 = 0.f, d1 = 0.f;
-    if (ng == 2 && ok) {
-      d0 = sc[31]; d1 = sc[32];
-      for (int j = 0; j < ni; j++) { d0 -= sc[25 + j] * rhs[j]; d1 -= sc[28 + j] * rhs[j]; }
-    }
-    if (!ok) a.flags[b] |= GCLM_STATUS_CHOLESKY_FAILED;
-    const int sl = a.slot[b];
-    const float* Pc = a.P + ((size_t)b * 2 + sl) * PSTRIDE;
-    float* Pn = a.P + ((size_t)b * 2 + (sl ^ 1)) * PSTRIDE;
-    float cam[8], g[3];
-    for (int i = 0; i < 8; i++) cam[i] = Pc[i];
-    for (int i = 0; i < 3; i++) g[i] = Pc[8 + i];
-    gravity_update(g, d0, d1, a.spherical);
-    int o = 0;
-    float df = 0.f;
-    if (a.est_focal) df = rhs[o++];
-    focal_update(cam, df, a.log_focal);
-    if (K > 0 && a.est_dist) dist_update(MODEL, cam, rhs + o);
-    for (int i = 0; i < 8; i++) Pn[i] = cam[i];
-    for (int i = 0; i < 3; i++) Pn[8 + i] = g[i];
-    a.slot[b] = sl ^ 1;
+  if (!ok) a.flags[b] |= GCLM_STATUS_CHOLESKY_FAILED;
+  const int sl = a.slot[b];
+  const float* Pc = a.P + ((size_t)b * 2 + sl) * PSTRIDE;
+  float* Pn = a.P + ((size_t)b * 2 + (sl ^ 1)) * PSTRIDE;
+  float cam[8], g[3];
+  for (int i = 0; i < 8; i++) cam[i] = Pc[i];
+  for (int i = 0; i < 3; i++) g[i] = Pc[8 + i];
+  gravity_update(g, d0, d1, a.spherical);
+  int o = 0;
+  float df = 0.f;
+  if (a.est_focal) df = rhs[o++];
+  focal_update(cam, df, a.log_focal);
+  if (K > 0 && a.est_dist) dist_update(MODEL, cam, rhs + o);
+  for (int i = 0; i < 8; i++) Pn[i] = cam[i];
+  for (int i = 0; i < 3; i++) Pn[8 + i] = g[i];
+  a.slot[b] = sl ^ 1;
+}
+
+// Batch-global stop of the shared solve (all images of all ranks converged): one thread, after the update.
+__device__ __forceinline__ void shared_stop_latch(const PassArgs& a, const float* sum_in) {
+  if (a.pass >= 1 && sum_in[24] == 0.f) {
+    if (a.pass < a.ctrl->stop_at) a.ctrl->stop_at = a.pass;
+    if (a.early_stop) a.ctrl->stop = 1;
   }
 }
 
-// Runs after shared_update_kernel of the same pass: latch the batch-global stop.
-__global__ void shared_stop_kernel(const PassArgs a, const float* sum_in) {
-  if (a.pass >= 1 && sum_in[24] == 0.f && a.early_stop) a.ctrl->stop = 1;
+// The tail of one shared-intrinsics LM step, run by the LAST CTA of the pass (block-wide call): ordered sum
+// of the per-image partials -> exchange with the peers over NVLink -> every image's update -> stop latch.
+// Replaces three kernel launches per step; the grid has drained by now, so this is the pass's critical tail.
+template <int MODEL>
+__device__ __noinline__ void shared_tail(const PassArgs& a, float (*s_part)[SCHUR_NSUM + 3], float* s_tot) {
+  __threadfence();  // the other CTAs' Schur partials (released before their image ticket)
+  float mine = schur_block_sum(a, s_part);
+  if (threadIdx.x < 32) {
+    if (a.pp.world > 1) mine = p2p_exchange(a, mine);
+    if (threadIdx.x < SCHUR_NSUM) { s_tot[threadIdx.x] = mine; a.shared_sums[threadIdx.x] = mine; }
+  }
+  __syncthreads();
+  if (*(volatile int*)&a.ctrl->comm_error) {
+    for (int b = threadIdx.x; b < a.B; b += blockDim.x) a.flags[b] |= GCLM_STATUS_COMM_TIMEOUT;
+    return;
+  }
+  for (int b = threadIdx.x; b < a.B; b += blockDim.x) shared_update_image<MODEL>(a, b, s_tot);
+  if (threadIdx.x == 0) shared_stop_latch(a, s_tot);
 }
+
+// ---- NCCL fallback (no peer memory): the same three steps as separate kernels around ncclAllReduce ----
+__global__ void shared_reduce_kernel(const __grid_constant__ PassArgs a) {  // launched with the pass kernel's block size
+  __shared__ float s_part[MAX_WARPS][SCHUR_NSUM + 3];
+  if (*(volatile int*)&a.ctrl->stop) return;
+  const float mine = schur_block_sum(a, s_part);
+  if (threadIdx.x < SCHUR_NSUM) a.shared_sums[threadIdx.x] = mine;
+}
+template <int MODEL>
+__global__ void shared_update_kernel(const __grid_constant__ PassArgs a) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (*(volatile int*)&a.ctrl->stop) return;
+  if (b < a.B) shared_update_image<MODEL>(a, b, a.shared_sums);
+}
+// Runs after shared_update_kernel of the same pass: latch the batch-global stop.
+__global__ void shared_stop_kernel(const __grid_constant__ PassArgs a) { shared_stop_latch(a, a.shared_sums); }
 
 // ---------------------------------------------------------------------------------------------
 // the fused pass kernel
@@ -584,6 +643,9 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
   __shared__ float s_red[MAX_WARPS][NACC];
   __shared__ float s_sum[NACC];
   __shared__ int s_last;
+  __shared__ int s_last_img;
+  __shared__ float s_part[MAX_WARPS][SCHUR_NSUM + 3];
+  __shared__ float s_tot[SCHUR_NSUM + 3];
   if (threadIdx.x == 0) {
     int sl = a.slot[b];
     if (a.is_final && a.ctrl->stop) sl ^= 1;
@@ -593,7 +655,7 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
   __syncthreads();
   const PassConst pc = s_pc;
   const FieldMask fm = {a.up != nullptr, a.lat != nullptr, a.uconf != nullptr, a.lconf != nullptr};
-  const float inv_up2 = 1.f / (a.up_scale * a.up_scale), inv_lat2 = 1.f / (a.lat_scale * a.lat_scale);
+  const RobustConst rc = make_robust_const(a.up_scale, a.lat_scale);
 
   extern __shared__ __align__(16) unsigned char dyn_smem[];
 #ifdef GCLM_TMA2D
@@ -650,6 +712,9 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
     float u[4];
 #pragma unroll
     for (int i = 0; i < 4; i++) u[i] = pixel_u(pc, x0 + i);
+#ifdef GCLM_HOIST
+    const RowCols<PACK> cols = make_row_cols<PACK>(pc, u);  // column-invariant terms, once per strip
+#endif
     const size_t off = (size_t)y0 * W + x0;
     const float* p_ux = (FULL || fm.up) ? a.up + (size_t)b * 2 * N + off : nullptr;
     const float* p_lat = (FULL || fm.lat) ? a.lat + (size_t)b * N + off : nullptr;
@@ -662,7 +727,11 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
       return;
 #endif
       // `ol` already holds target_lat = sin(latitude_field): sin_plane_kernel ran once before pass 0
-      row_accumulate<MODEL, GEN_D, FULL, PACK>(pc, fm, u, pixel_v(pc, y), ox, oy, ol, cu, cl, inv_up2, inv_lat2, acc);
+#ifdef GCLM_HOIST
+      row_accumulate<MODEL, GEN_D, FULL, PACK>(pc, fm, cols, pixel_v(pc, y), ox, oy, ol, cu, cl, rc, acc);
+#else
+      row_accumulate<MODEL, GEN_D, FULL, PACK>(pc, fm, make_row_cols<PACK>(pc, u), pixel_v(pc, y), ox, oy, ol, cu, cl, rc, acc);
+#endif
     };
 #ifdef GCLM_TMA2D
     if constexpr (FULL) {
@@ -838,8 +907,21 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
   }
   if (threadIdx.x == 0) {
     a.tickets[b] = 0u;
-    if (a.shared && !a.is_final) schur_image<MODEL>(a, b, s_sum);
-    else lm_step_image<MODEL>(a, b, s_sum);
+    finish_sums<MODEL, GEN_D>(s_sum, pc.k1, pc.k2, a.up_scale);  // [g0 g1 X k..] x 1/a_up -> [g0 g1 f k..]
+    s_last_img = 0;
+    if (a.shared && !a.is_final) {
+      schur_image<MODEL>(a, b, s_sum);
+      if (a.fused_shared) {  // image-level ticket: the last image's CTA finishes the LM step for the batch
+        __threadfence();
+        if (atomicAdd(&a.ctrl->img_done, 1u) == (unsigned)a.B - 1u) { a.ctrl->img_done = 0u; s_last_img = 1; }
+      }
+    } else {
+      lm_step_image<MODEL>(a, b, s_sum);
+    }
+  }
+  if (a.shared && a.fused_shared && !a.is_final) {  // uniform over the grid
+    __syncthreads();
+    if (s_last_img) shared_tail<MODEL>(a, s_part, s_tot);
   }
 }
 
@@ -852,6 +934,7 @@ __global__ void lm_init_kernel(PassArgs a, const float* cam0, const float* g0) {
     a.ctrl->stop = 0; a.ctrl->stop_at = a.num_steps;
     a.ctrl->done[0] = a.ctrl->done[1] = 0u;
     a.ctrl->unconv[0] = a.ctrl->unconv[1] = 0u;
+    a.ctrl->img_done = 0u; a.ctrl->comm_error = 0;
   }
   if (b >= a.B) return;
   float* P0 = a.P + (size_t)b * 2 * PSTRIDE;
@@ -1554,40 +1637,43 @@ int gclm_solve_shared(gclm_handle* h, const gclm_problem* prob, const gclm_optio
   PassArgs a = make_args(h, prob, opt, res, t, L);
   a.shared = 1;
   a.stop_mode = GCLM_STOP_BATCH;  // shared intrinsics couple all images: the criterion is global
-  float* sums = a.schur + (size_t)prob->batch * SCHUR_STRIDE;  // 26 floats after the partials
+  a.shared_sums = a.schur + (size_t)prob->batch * SCHUR_STRIDE;  // SCHUR_NSUM + 1 floats after the partials
+  const bool multi = comm && comm->world > 1;
+  const bool p2p = multi && comm->p2p_ready;
+  a.fused_shared = (!multi || p2p) ? 1 : 0;  // the LM step ends inside the pass kernel (one launch per step)
+  memset(&a.pp, 0, sizeof(a.pp));
+  if (p2p) {
+    a.pp.world = comm->world; a.pp.rank = comm->rank;
+    for (int r = 0; r < comm->world; r++) a.pp.peer[r] = comm->peer[r];
+  }
   const bool full = a.up && a.lat && a.uconf && a.lconf;
   const unsigned bblocks = (unsigned)((prob->batch + 127) / 128);
   lm_init_kernel<<<bblocks, 128, 0, s>>>(a, prob->camera_init, prob->gravity_init);
   h->launches++;
   launch_sin_plane(h, prob, a, s);
   const dim3 grid((unsigned)((size_t)prob->batch * t.tiles_per_image)), block(t.nwarps * 32);
-  PassTimer timer(h, s, opt->num_steps + 1);  // here the bracket also holds the O(B) Schur kernels
+  PassTimer timer(h, s, opt->num_steps + 1);  // here the bracket also holds the per-step tail (reduce, exchange, update)
   for (int it = 0; it < opt->num_steps; it++) {
     a.pass = it; a.is_final = 0;
+    if (p2p) a.pp.seq = ++comm->seq;
     launch_pass(h, a, !opt->use_log_focal, full, grid, block, s);
-    P2PArgs pp;
-    memset(&pp, 0, sizeof(pp));
-    const bool p2p = comm && comm->world > 1 && comm->p2p_ready;
-    if (p2p) {
-      pp.world = comm->world; pp.rank = comm->rank; pp.seq = ++comm->seq;
-      for (int r = 0; r < comm->world; r++) pp.peer[r] = comm->peer[r];
-    }
-    shared_reduce_kernel<<<1, 1024, 0, s>>>(a, sums, pp);
-    if (nccl && !p2p) {
-      const int rc = nccl->all_reduce(sums, sums, SCHUR_NSUM, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm->comm, s);
-      if (rc != 0) {
-        snprintf(h->last_error, sizeof(h->last_error), "ncclAllReduce: %s",
-                 nccl->get_error_string ? nccl->get_error_string(rc) : "error");
-        return GCLM_ERR_NCCL;
-      }
+    h->launches++;
+    if (a.fused_shared) continue;
+    // ---- fallback without peer memory: reduce -> ncclAllReduce -> update -> stop latch ----
+    shared_reduce_kernel<<<1, block, 0, s>>>(a);
+    const int rc = nccl->all_reduce(a.shared_sums, a.shared_sums, SCHUR_NSUM, /*ncclFloat32*/ 7, /*ncclSum*/ 0, comm->comm, s);
+    if (rc != 0) {
+      snprintf(h->last_error, sizeof(h->last_error), "ncclAllReduce: %s",
+               nccl->get_error_string ? nccl->get_error_string(rc) : "error");
+      return GCLM_ERR_NCCL;
     }
     switch (a.model) {
-      case PINHOLE: shared_update_kernel<PINHOLE><<<bblocks, 128, 0, s>>>(a, sums); break;
-      case SIMPLE_RADIAL: shared_update_kernel<SIMPLE_RADIAL><<<bblocks, 128, 0, s>>>(a, sums); break;
-      case RADIAL: shared_update_kernel<RADIAL><<<bblocks, 128, 0, s>>>(a, sums); break;
-      default: shared_update_kernel<SIMPLE_DIVISIONAL><<<bblocks, 128, 0, s>>>(a, sums); break;
+      case PINHOLE: shared_update_kernel<PINHOLE><<<bblocks, 128, 0, s>>>(a); break;
+      case SIMPLE_RADIAL: shared_update_kernel<SIMPLE_RADIAL><<<bblocks, 128, 0, s>>>(a); break;
+      case RADIAL: shared_update_kernel<RADIAL><<<bblocks, 128, 0, s>>>(a); break;
+      default: shared_update_kernel<SIMPLE_DIVISIONAL><<<bblocks, 128, 0, s>>>(a); break;
     }
-    shared_stop_kernel<<<1, 1, 0, s>>>(a, sums);
+    shared_stop_kernel<<<1, 1, 0, s>>>(a);
     h->launches += 4;
   }
   a.pass = opt->num_steps; a.is_final = 1;

@@ -63,6 +63,7 @@ typedef enum {
 #define GCLM_STATUS_CHOLESKY_FAILED 1u /* lm_optimizer.py:129-133 (per image here) */
 #define GCLM_STATUS_COV_SINGULAR 2u    /* torch.inverse would have raised (lm_optimizer.py:484) */
 #define GCLM_STATUS_NONFINITE 4u
+#define GCLM_STATUS_COMM_TIMEOUT 8u /* shared intrinsics, fused exchange: a peer never contributed; the solve was aborted */
 
 typedef struct gclm_handle gclm_handle;
 
@@ -172,8 +173,11 @@ int gclm_system(gclm_handle* h, const gclm_problem* prob, const gclm_options* op
  * 599-603): one focal / distortion for the whole batch, per-image gravity.  The dense
  * (2B+n_i)^2 arrow system of the reference is solved through its Schur complement.
  * `comm` is NULL for a single GPU, else a handle from gclm_comm_create: the batch is then the
- * union of all ranks' batches and one all-reduce of <= 2 n_i^2 + 2 n_i + 2 floats is issued per
- * LM step on `cuda_stream`.
+ * union of all ranks' batches and one all-reduce of <= 2 n_i^2 + 2 n_i + 2 floats is done per LM step.
+ * With peer memory attached (gclm_comm_p2p_*) or on a single GPU the whole LM step -- ordered sum of
+ * the per-image partials, exchange over NVLink, every image's update, stop latch -- runs in the
+ * epilogue of the pass kernel's last CTA: num_steps + 1 pass launches per solve.  Without peer memory
+ * three small kernels and one ncclAllReduce follow every pass.
  */
 typedef struct gclm_comm gclm_comm;
 int gclm_solve_shared(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt,

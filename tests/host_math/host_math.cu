@@ -22,7 +22,7 @@ void run(const PassConst& pc, const Fields& f, float up_scale, float lat_scale, 
   using V = typename std::conditional<PACK, f2, float>::type;
   constexpr int NACC = Dims<MODEL>::NACC;
   const FieldMask fm = {true, true, true, true};
-  const float inv_up2 = 1.f / (up_scale * up_scale), inv_lat2 = 1.f / (lat_scale * lat_scale);
+  const RobustConst rc = make_robust_const(up_scale, lat_scale);
   const size_t N = (size_t)f.H * f.W;
   for (int k = 0; k < NACC; k++) out[k] = 0.0;
   for (int y = 0; y < f.H; y++) {
@@ -38,10 +38,12 @@ void run(const PassConst& pc, const Fields& f, float up_scale, float lat_scale, 
       const float4 cl = make_float4(f.lconf[o], f.lconf[o + 1], f.lconf[o + 2], f.lconf[o + 3]);
       V acc[NACC];
       for (int k = 0; k < NACC; k++) acc[k] = splat<V>(0.f);
-      row_accumulate<MODEL, GEN_D, true, PACK>(pc, fm, u, pixel_v(pc, y), ox, oy, ol, cu, cl, inv_up2, inv_lat2, acc);
+      row_accumulate<MODEL, GEN_D, true, PACK>(pc, fm, make_row_cols<PACK>(pc, u), pixel_v(pc, y), ox, oy, ol, cu, cl, rc, acc);
       for (int k = 0; k < NACC; k++) out[k] += (double)hsum(acc[k]);  // fp64 sum: only the pixel math is tested
     }
   }
+  // what the kernel's per-image epilogue does to the reduced sums before the solver sees them
+  finish_sums<MODEL, GEN_D, double>(out, pc.k1, pc.k2, up_scale);
 }
 
 template <int MODEL>

@@ -113,8 +113,15 @@ def test_bench_workload_slice_vs_oracle(dev, model, B, h, w, conf):
     ref = oracle.lm(model, fn["up_field"], fn["latitude_field"], fn["up_confidence"], fn["latitude_confidence"],
                     conf=conf)
     cam, grav = out["camera"]._data.cpu().numpy(), out["gravity"]._data.cpu().numpy()
+    stop = out["stop_at"].cpu().numpy()
+    assert np.abs(stop - ref["stop_at"]).max() <= 1
+    if conf.get("early_stop", True) and np.any(stop != ref["stop_at"]):
+        # the batch-global criterion |cost_i - cost_{i-1}| <= 1e-8 (1 + |cost|) on fp32 costs ~1e-4 can fire one
+        # iteration apart; slowly converging images (fisheye k1) still move ~1e-4 in that step, so compare at
+        # the SAME iteration count: the oracle re-run for exactly the engine's number of steps
+        ref = oracle.lm(model, fn["up_field"], fn["latitude_field"], fn["up_confidence"], fn["latitude_confidence"],
+                        conf={**conf, "num_steps": int(stop.max()), "early_stop": False})
     assert_params_close(cam, grav, ref["camera"], ref["gravity"], model, tol=TOL)
-    assert np.abs(out["stop_at"].cpu().numpy() - ref["stop_at"]).max() <= 1
     np.testing.assert_allclose(out["final_cost"].cpu().numpy(), ref["final_cost"], rtol=2e-4)
     # the calibration is also RIGHT (not just equal): focal within 2 % of the synthetic ground truth
     assert np.median(np.abs(cam[:, 3] / cam_gt[:, 3] - 1)) < 0.02

@@ -87,6 +87,31 @@ __global__ void __launch_bounds__(256) k(float* out, long long* cyc, float x, fl
       for (int i = 0; i < 8; i++) p[i] = __fmul2_rn(p[i], x2);
 #pragma unroll
       for (int i = 0; i < 8; i++) a[i] = fmaf(a[i], x, y);
+    } else if (MODE == 21) {  // 8 FFMA2 + 8 FMUL2
+#pragma unroll
+      for (int i = 0; i < 8; i++) p[i] = __ffma2_rn(p[i], x2, y2);
+#pragma unroll
+      for (int i = 0; i < 8; i++) q[i] = __fmul2_rn(q[i], x2);
+    } else if (MODE == 22) {  // 4 FFMA2 + 16 FFMA
+#pragma unroll
+      for (int i = 0; i < 4; i++) p[i] = __ffma2_rn(p[i], x2, y2);
+#pragma unroll
+      for (int i = 0; i < 16; i++) a[i] = fmaf(a[i], x, y);
+    } else if (MODE == 23) {  // 8 FFMA2 + 8 FADD2
+#pragma unroll
+      for (int i = 0; i < 8; i++) p[i] = __ffma2_rn(p[i], x2, y2);
+#pragma unroll
+      for (int i = 0; i < 8; i++) q[i] = __fadd2_rn(q[i], y2);
+    } else if (MODE == 24) {  // 16 FMUL2
+#pragma unroll
+      for (int i = 0; i < 8; i++) p[i] = __fmul2_rn(p[i], x2);
+#pragma unroll
+      for (int i = 0; i < 8; i++) q[i] = __fmul2_rn(q[i], x2);
+    } else if (MODE == 25) {  // 8 FMUL2 + 16 FFMA
+#pragma unroll
+      for (int i = 0; i < 8; i++) p[i] = __fmul2_rn(p[i], x2);
+#pragma unroll
+      for (int i = 0; i < 16; i++) a[i] = fmaf(a[i], x, y);
     } else if (MODE == 9) {  // 8 FFMA2, all operands packed register pairs (no broadcast)
 #pragma unroll
       for (int i = 0; i < 8; i++) p[i] = __ffma2_rn(p[i], q[i], r[i]);
@@ -143,7 +168,12 @@ void run(const char* name, int instr_per_iter, int ctas_per_sm) {
 }
 
 int main() {
-  for (int c : {4}) {
+  for (int c : {2, 4}) {
+    run<21>("8 FFMA2 + 8 FMUL2", 16, c);
+    run<22>("4 FFMA2 + 16 FFMA", 20, c);
+    run<23>("8 FFMA2 + 8 FADD2", 16, c);
+    run<24>("16 FMUL2", 16, c);
+    run<25>("8 FMUL2 + 16 FFMA", 24, c);
     run<14>("8 FFMA2 + 8 FFMA", 16, c);
     run<15>("8 FFMA2 + 8 FMUL", 16, c);
     run<16>("8 FFMA2 + 8 FADD", 16, c);
