@@ -548,6 +548,35 @@ def time_workload(args, workload, wl, ctx, *, with_e2e, with_parity):
                 "step_frac": bytes_per_launch * passes / (ms_per_step * 1e-3) / 1e9 / peak,
                 "timed_launches": pass_launches}
 
+    # ---- small batches (the calibrate() case): latency of one solve replayed from a CUDA graph ----
+    graph = None
+    if B <= 8 and not shared:
+        eng.reserve(B, h, w)
+        static = {k: v.clone() for k, v in fields.items()}
+        with torch.no_grad():
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                opt(static)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                gout = opt(static)
+            for _ in range(10):
+                g.replay()
+            torch.cuda.synchronize()
+            reps = 200
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+        graph = {"us_per_solve": 1e3 * e0.elapsed_time(e1) / reps, "replays": reps,
+                 "schedule": "persistent (one cooperative launch for all passes)" if eng.persistent_count else "per pass",
+                 "equal_to_eager": bool(torch.equal(gout["camera"]._data, out["camera"]._data))}
+        del static, gout, g
+
     # ---- end to end: host (pinned) buffers -> H2D -> solve -> D2H, pipelined in chunks ----
     e2e = None
     if with_e2e and not shared:
@@ -573,7 +602,7 @@ def time_workload(args, workload, wl, ctx, *, with_e2e, with_parity):
     opt.comm = None
     torch.cuda.empty_cache()
     return {"value": value, "ms_per_step": ms_per_step, "roofline": roofline, "e2e": e2e, "clocks": clocks,
-            "launches": int(launches), "f_err": f_err, "parity": parity, "collective": collective}
+            "launches": int(launches), "f_err": f_err, "parity": parity, "collective": collective, "graph": graph}
 
 
 def main():
@@ -658,6 +687,8 @@ def main():
             "roofline": main_rec["roofline"], "parity": main_rec["parity"], "shared": shared_rec,
             "cpu_baseline": cpu, "median_focal_error_vs_gt": main_rec["f_err"],
         }
+        if main_rec["graph"]:
+            line["graph_replay"] = main_rec["graph"]
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

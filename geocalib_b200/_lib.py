@@ -20,6 +20,7 @@ LIB_PATH = Path(_os.environ["GCLM_LIB"]) if _os.environ.get("GCLM_LIB") else CSR
 
 GCLM_OK = 0
 STOP_BATCH, STOP_PER_IMAGE = 0, 1
+SCHEDULE_AUTO, SCHEDULE_PER_PASS, SCHEDULE_PERSISTENT = 0, 1, 2
 STATUS_CHOLESKY_FAILED, STATUS_COV_SINGULAR, STATUS_NONFINITE, STATUS_COMM_TIMEOUT = 1, 2, 4, 8
 COMM_ID_BYTES = 128
 IPC_HANDLE_BYTES = 64
@@ -49,7 +50,7 @@ class Options(ctypes.Structure):
         ("use_spherical_manifold", c_int32), ("use_log_focal", c_int32),
         ("up_loss_fn_scale", c_float), ("lat_loss_fn_scale", c_float),
         ("stop_mode", c_int32), ("compute_uncertainty", c_int32), ("rows_per_tile", c_int32),
-        ("reserved", c_int32 * 3),
+        ("schedule", c_int32), ("reserved", c_int32 * 2),
     ]
 
 
@@ -81,6 +82,7 @@ SIGNATURES = {
     "gclm_comm_p2p_disable": (c_int, [c_void_p]),
     "gclm_solve_host": (c_int, [c_void_p, POINTER(Problem), POINTER(Options), POINTER(Result), c_int]),
     "gclm_launch_count": (c_int64, [c_void_p]),
+    "gclm_persistent_count": (c_int64, [c_void_p]),
     "gclm_tile_config": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, POINTER(c_int32)]),
     "gclm_pass_timing": (c_int, [c_void_p, c_int]),
     "gclm_pass_time": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_int64)]),

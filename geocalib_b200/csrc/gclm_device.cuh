@@ -163,12 +163,14 @@ struct PassConst {
 // Per-launch constants of the robust loss with the scale folded in (see the header comment).
 struct RobustConst {
   float up_s2, up_2os, lat_s2, lat_2os, lat_ratio;  // a^2, 2/a for both residuals; a_lat / a_up
+  float up_inv2, lat_inv2;                          // 1/a^2 (unfolded form)
 };
 GCLM_HD inline RobustConst make_robust_const(float up_scale, float lat_scale) {
   RobustConst rc;
   rc.up_s2 = up_scale * up_scale; rc.up_2os = 2.f / up_scale;
   rc.lat_s2 = lat_scale * lat_scale; rc.lat_2os = 2.f / lat_scale;
   rc.lat_ratio = lat_scale / up_scale;
+  rc.up_inv2 = 1.f / rc.up_s2; rc.lat_inv2 = 1.f / rc.lat_s2;
   return rc;
 }
 
@@ -355,6 +357,23 @@ GCLM_HD __forceinline__ void model_scalars(const PassConst& pc, V r2, ModelScala
 // ------------------------------------------------------------------------------------------
 struct FieldMask { bool up, lat, up_conf, lat_conf; };
 
+// A/B knobs (profiles/r2_ab_*.txt).  Pinhole sits at the 128-register cap of its 2 x 8-warp CTA shape: keeping
+// the column-invariant terms live across the row loop costs it more in register moves than the FMAs it saves
+// (0.97 -> 0.92 of the roofline), so by default only the distortion models (168 registers) use those forms.
+#ifndef GCLM_PIN_GEOM_NEW
+#define GCLM_PIN_GEOM_NEW 0
+#endif
+#ifndef GCLM_PIN_HUBER_NEW
+#define GCLM_PIN_HUBER_NEW 1
+#endif
+#ifndef GCLM_DIST_COLS
+#define GCLM_DIST_COLS 1
+#endif
+template <int MODEL> struct Forms {
+  static constexpr bool COLS = MODEL != PINHOLE ? GCLM_DIST_COLS != 0 : GCLM_PIN_GEOM_NEW != 0;  // column-invariant forms (LICM food)
+  static constexpr bool HUBER = MODEL != PINHOLE || GCLM_PIN_HUBER_NEW;    // scale-folded Huber
+};
+
 // accumulator update a*b + c: packed by default; -DGCLM_SCALAR_ACC issues it as two scalar FFMA (A/B knob)
 GCLM_HD __forceinline__ float fma_acc(float a, float b, float c) { return ::fmaf(a, b, c); }
 GCLM_HD __forceinline__ f2 fma_acc(f2 a, f2 b, f2 c) {
@@ -392,7 +411,9 @@ GCLM_HD __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMa
   // directly and (LIT, k1 != 0) moved into the X basis; K0 means k1 == 0, where X == f
   constexpr bool DIRECT_F = GEN_D || K0 || LIT;
   const bool has_up = FULL || fm.up, has_lat = FULL || fm.lat;
-  const V r2 = (u * u) + splat<V>(v * v);  // u*u is column-invariant: the compiler hoists it out of the row loop
+  V r2;
+  if constexpr (Forms<MODEL>::COLS) r2 = (u * u) + splat<V>(v * v);  // u*u is column-invariant: hoisted out of the row loop
+  else r2 = fmaf(u, u, splat<V>(v * v));
   ModelScalars<K, V> m;
   model_scalars<MODEL, V, LIT, K0>(pc, r2, m);
 
@@ -403,12 +424,13 @@ GCLM_HD __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMa
   if constexpr (GEN_D) { dx = -(u * pc.dsx); dy = -v * pc.dsy; uvd = fmaf(u, dx, splat<V>(v * dy)); }
 
   if (has_up) {  // ---- up field: perspective_fields.py:47-182 ----
-    const V p0x = col.p0x;
+    const V p0x = Forms<MODEL>::COLS ? col.p0x : fmaf(-pc.c, u, splat<V>(pc.a));
     const float p0y = fmaf(-pc.c, v, pc.b);
     const float zy0 = fmaf(-pc.T20, v, pc.T10), zy1 = fmaf(-pc.T21, v, pc.T11);  // row-uniform
     V px = p0x, py = splat<V>(p0y), iota = splat<V>(0.f);
     if constexpr (K > 0) {
-      iota = (u * p0x) + splat<V>(v * p0y);  // column-invariant + row-uniform
+      if constexpr (Forms<MODEL>::COLS) iota = (u * p0x) + splat<V>(v * p0y);  // column-invariant + row-uniform
+      else iota = fmaf(u, p0x, splat<V>(v * p0y));
       const V pi = m.phi * iota;
       px = fmaf(m.s, p0x, pi * u);
       py = fmaf(m.s, splat<V>(p0y), pi * v);
@@ -423,13 +445,24 @@ GCLM_HD __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMa
     e = fmaf(upx, oy, -(upy * ox));
     // Huber (lm_optimizer.py:79-87; chi + 1e-8 == chi in fp32 for chi > 1), scale folded in
     const V c2 = fmaf(rx, rx, ry * ry);
-    const V isx = fast_rsqrt(fmaxf(c2, rc.up_s2));
-    w_up = isx * cu;
-    acc[NH + NF] = fmaf(c2 * w_up, rc.up_2os - isx, acc[NH + NF]);
+    if constexpr (Forms<MODEL>::HUBER) {
+      const V isx = fast_rsqrt(fmaxf(c2, rc.up_s2));
+      w_up = isx * cu;
+      acc[NH + NF] = fmaf(c2 * w_up, rc.up_2os - isx, acc[NH + NF]);
+    } else {  // cost*conf = 2 chi w - min(chi,1) conf, w = conf/sqrt(max(chi,1)); unscaled weights (finish_sums: x1)
+      const V chi = c2 * rc.up_inv2;
+      const V isx = fast_rsqrt(fmaxf(chi, 1.f));
+      w_up = isx * cu;
+      acc[NH + NF] = fmaf(chi + chi, w_up, fmaf(-fminf(chi, 1.f), cu, acc[NH + NF]));
+    }
     // Jacobian columns.  With M z = s z + phi uv (uv.z) and z_j = (T0j - u T2j, T1j - v T2j):
     //   s_j = T0j alpha + T1j beta - T2j gamma,  alpha = s Ap + phi Nu u, beta = s Bp + phi Nu v,
     //   gamma = alpha u + beta v = Nu (s + phi r^2)        (Nu = Ap u + Bp v)
-    if constexpr (K == 0) {
+    if constexpr (K == 0 && !Forms<MODEL>::COLS) {
+      su_[0] = fmaf(Ap, pc.T00, fmaf(Bp, pc.T10, -pc.T20 * Nu));
+      su_[1] = fmaf(Ap, pc.T01, fmaf(Bp, pc.T11, -pc.T21 * Nu));
+      su_[2] = GEN_D ? -pc.c * fmaf(Ap, dx, Bp * dy) : pc.c * Nu;
+    } else if constexpr (K == 0) {
       su_[0] = fmaf(Ap, col.zx0, Bp * zy0);
       su_[1] = fmaf(Ap, col.zx1, Bp * zy1);
       if constexpr (!GEN_D) su_[2] = pc.c * Nu;
@@ -439,8 +472,13 @@ GCLM_HD __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMa
       const V alpha = fmaf(pn, u, m.s * Ap), beta = fmaf(pn, v, m.s * Bp);
       const V pr2 = m.phi * r2;
       const V gamma = Nu * (m.s + pr2);
-      su_[0] = fmaf(alpha, col.zx0, beta * zy0);
-      su_[1] = fmaf(alpha, col.zx1, beta * zy1);
+      if constexpr (Forms<MODEL>::COLS) {
+        su_[0] = fmaf(alpha, col.zx0, beta * zy0);
+        su_[1] = fmaf(alpha, col.zx1, beta * zy1);
+      } else {
+        su_[0] = fmaf(alpha, pc.T00, fmaf(beta, pc.T10, -pc.T20 * gamma));
+        su_[1] = fmaf(alpha, pc.T01, fmaf(beta, pc.T11, -pc.T21 * gamma));
+      }
       const V Np0 = fmaf(Ap, p0x, Bp * p0y);  // (n_perp . p0)/rho
       const V iN = iota * Nu;
 #pragma unroll
@@ -462,7 +500,8 @@ GCLM_HD __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMa
   }
 
   if (has_lat) {  // ---- latitude field: perspective_fields.py:185-275 ----
-    const V S = (pc.a * u) + splat<V>(pc.b * v);  // column-invariant + row-uniform
+    const V S = Forms<MODEL>::COLS ? (pc.a * u) + splat<V>(pc.b * v)  // column-invariant + row-uniform
+                                   : fmaf(pc.a, u, splat<V>(pc.b * v));
     V m2, ln;
     if constexpr (K == 0) { m2 = r2 + 1.f; ln = S + pc.c; }
     else { m2 = fmaf(m.su * m.su, r2, splat<V>(1.f)); ln = fmaf(m.su, S, splat<V>(pc.c)); }
@@ -471,16 +510,31 @@ GCLM_HD __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMa
     const V lc = fminf(fmaxf(l, -1.f + 1e-6f), 1.f - 1e-6f);
     r_lat = sin_olat - lc;  // lm_optimizer.py:270-271
     const V c2 = r_lat * r_lat;
-    const V isx = fast_rsqrt(fmaxf(c2, rc.lat_s2));
-    w_lat = isx * cl;
-    acc[NH + NF + 1] = fmaf(c2 * w_lat, rc.lat_2os - isx, acc[NH + NF + 1]);
-    if (rc.lat_ratio != 1.f) w_lat = w_lat * rc.lat_ratio;  // both residuals share the a_up of finish_sums
-    if constexpr (K == 0) {
+    if constexpr (Forms<MODEL>::HUBER) {
+      const V isx = fast_rsqrt(fmaxf(c2, rc.lat_s2));
+      w_lat = isx * cl;
+      acc[NH + NF + 1] = fmaf(c2 * w_lat, rc.lat_2os - isx, acc[NH + NF + 1]);
+      if (rc.lat_ratio != 1.f) w_lat = w_lat * rc.lat_ratio;  // both residuals share the a_up of finish_sums
+    } else {
+      const V chi = c2 * rc.lat_inv2;
+      const V isx = fast_rsqrt(fmaxf(chi, 1.f));
+      w_lat = isx * cl;
+      acc[NH + NF + 1] = fmaf(chi + chi, w_lat, fmaf(-fminf(chi, 1.f), cl, acc[NH + NF + 1]));
+    }
+    if constexpr (K == 0 && !Forms<MODEL>::COLS) {
+      sl_[0] = im * fmaf(pc.T00, u, splat<V>(fmaf(pc.T10, v, pc.T20)));
+      sl_[1] = im * fmaf(pc.T01, u, splat<V>(fmaf(pc.T11, v, pc.T21)));
+    } else if constexpr (K == 0) {
       sl_[0] = im * ((pc.T00 * u) + splat<V>(fmaf(pc.T10, v, pc.T20)));
       sl_[1] = im * ((pc.T01 * u) + splat<V>(fmaf(pc.T11, v, pc.T21)));
     } else {
-      sl_[0] = im * fmaf(m.su, (pc.T00 * u) + splat<V>(pc.T10 * v), splat<V>(pc.T20));
-      sl_[1] = im * fmaf(m.su, (pc.T01 * u) + splat<V>(pc.T11 * v), splat<V>(pc.T21));
+      if constexpr (Forms<MODEL>::COLS) {
+        sl_[0] = im * fmaf(m.su, (pc.T00 * u) + splat<V>(pc.T10 * v), splat<V>(pc.T20));
+        sl_[1] = im * fmaf(m.su, (pc.T01 * u) + splat<V>(pc.T11 * v), splat<V>(pc.T21));
+      } else {
+        sl_[0] = im * fmaf(m.su, fmaf(pc.T00, u, splat<V>(pc.T10 * v)), splat<V>(pc.T20));
+        sl_[1] = im * fmaf(m.su, fmaf(pc.T01, u, splat<V>(pc.T11 * v)), splat<V>(pc.T21));
+      }
     }
     const V li = l * im;
     if constexpr (!GEN_D) {
@@ -572,7 +626,8 @@ GCLM_HD inline void finish_sums(T* s, float k1, float k2, float up_scale) {
     for (int i = 0; i < NF; i++)
       for (int j = i; j < NF; j++) s[idx++] = Hf[i][j];
   }
-  for (int i = 0; i < NH + NF; i++) s[i] *= (T)up_scale;
+  if constexpr (Forms<MODEL>::HUBER)
+    for (int i = 0; i < NH + NF; i++) s[i] *= (T)up_scale;
 }
 
 // simple_divisional: does pixel (u, v) need the literal masked formulas?  k1 == 0 (trivial init:

@@ -49,6 +49,10 @@ constexpr int RING_STAGES = GCLM_RING_STAGES;  // rows prefetched per lane by th
 constexpr int SCHUR_STRIDE = 48;
 constexpr int SCHUR_NSUM = 25;
 
+// Which pass a CTA is working on: a kernel parameter for the one-launch-per-pass schedule, a loop variable in
+// the persistent small-batch kernel.
+struct PassId { int pass, is_final; };
+
 struct Ctrl {
   int stop;            // batch-global early stop fired: later LM passes are no-ops
   int stop_at;         // first iteration (1-based) at which all images were converged
@@ -56,6 +60,7 @@ struct Ctrl {
   unsigned unconv[2];  // images NOT converged in the current pass
   unsigned img_done;   // shared intrinsics: images whose Schur partials of this pass are written
   int comm_error;      // sticky: a peer's contribution never arrived (fused exchange timed out)
+  unsigned bar;        // persistent kernel: grid barrier arrivals (monotone within a solve)
 };
 
 // One-shot all-reduce over NVLink peer memory, fused into the pass kernel's epilogue: every rank stores its
@@ -247,9 +252,9 @@ __device__ __forceinline__ bool allclose1(float nw, float prev, float atol, floa
 
 // Batch-global early-stop bookkeeping (lm_optimizer.py:90-92, 619-625): the last image to finish
 // this pass knows whether ALL images were converged.
-__device__ __forceinline__ void batch_stop_vote(const PassArgs& a, bool converged) {
+__device__ __forceinline__ void batch_stop_vote(const PassArgs& a, const PassId pid, bool converged) {
   Ctrl* c = a.ctrl;
-  const int par = a.pass & 1;
+  const int par = pid.pass & 1;
   if (!converged) atomicAdd(&c->unconv[par], 1u);
   __threadfence();
   const unsigned t = atomicAdd(&c->done[par], 1u);
@@ -257,7 +262,7 @@ __device__ __forceinline__ void batch_stop_vote(const PassArgs& a, bool converge
     __threadfence();
     const unsigned un = atomicAdd(&c->unconv[par], 0u);
     if (un == 0u) {
-      if (a.pass < c->stop_at) c->stop_at = a.pass;  // infos["stop_at"] = min(i + 1, ...)
+      if (pid.pass < c->stop_at) c->stop_at = pid.pass;  // infos["stop_at"] = min(i + 1, ...)
       if (a.early_stop) c->stop = 1;
     }
     c->done[par ^ 1] = 0u;  // arm the counters of the next pass
@@ -267,10 +272,10 @@ __device__ __forceinline__ void batch_stop_vote(const PassArgs& a, bool converge
 }
 
 template <int MODEL>
-__device__ __noinline__ void lm_step_image(const PassArgs& a, int b, const float* sums) {
+__device__ __noinline__ void lm_step_image(const PassArgs& a, const PassId pid, int b, const float* sums) {
   constexpr int K = Dims<MODEL>::K, NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH;
   int sl = a.slot[b];
-  if (a.is_final) {
+  if (pid.is_final) {
     if (a.sys_h) {  // gclm_system: hand the reduced system out as it is (full columns [g0 g1 f k..])
       const float invN = 1.f / ((float)a.H * (float)a.Wt);
       int idx = 0;
@@ -297,7 +302,7 @@ __device__ __noinline__ void lm_step_image(const PassArgs& a, int b, const float
   const float cost = cu + cl;  // lm_optimizer.py:584,610
   float lam = a.lam[b];
   bool converged = false;
-  if (a.pass == 0) {
+  if (pid.pass == 0) {
     a.cost0[b * 3] = cost; a.cost0[b * 3 + 1] = cu; a.cost0[b * 3 + 2] = cl;
   } else {
     // this pass evaluated cost(theta_i) == "new_cost" of iteration i-1 (lm_optimizer.py:607-613)
@@ -305,7 +310,7 @@ __device__ __noinline__ void lm_step_image(const PassArgs& a, int b, const float
     if (!a.fix_lambda) lam = fminf(fmaxf(lam * (cost > prev ? 10.f : 0.1f), 1e-6f), 1e2f);
     converged = allclose1(cost, prev, a.atol, a.rtol);
     if (a.stop_mode == GCLM_STOP_PER_IMAGE && converged) {
-      if (a.pass < a.stop_at[b]) a.stop_at[b] = a.pass;
+      if (pid.pass < a.stop_at[b]) a.stop_at[b] = pid.pass;
       if (a.early_stop) {  // freeze: theta_i is final, no further work on this image
         a.flags[b] |= FLAG_FROZEN;
         a.prev_cost[b] = cost;
@@ -353,7 +358,7 @@ __device__ __noinline__ void lm_step_image(const PassArgs& a, int b, const float
   for (int i = 0; i < 3; i++) Pn[8 + i] = g[i];
   a.slot[b] = sl ^ 1;
   if (a.stop_mode == GCLM_STOP_BATCH) {
-    if (a.pass >= 1) batch_stop_vote(a, converged);
+    if (pid.pass >= 1) batch_stop_vote(a, pid, converged);
   }
 }
 
@@ -367,14 +372,14 @@ __device__ __noinline__ void lm_step_image(const PassArgs& a, int b, const float
 // <= 25 sums cross images (and GPUs): one tiny all-reduce per LM step.
 // ---------------------------------------------------------------------------------------------
 template <int MODEL>
-__device__ __noinline__ void schur_image(const PassArgs& a, int b, const float* sums) {
+__device__ __noinline__ void schur_image(const PassArgs& a, const PassId pid, int b, const float* sums) {
   constexpr int NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH;
   const float invN = 1.f / ((float)a.H * (float)a.Wt);
   const float cu = sums[NH + NF] * (a.up_scale * a.up_scale) * invN;
   const float cl = sums[NH + NF + 1] * (a.lat_scale * a.lat_scale) * invN;
   const float cost = cu + cl;
   bool converged = false;
-  if (a.pass == 0) { a.cost0[b * 3] = cost; a.cost0[b * 3 + 1] = cu; a.cost0[b * 3 + 2] = cl; }
+  if (pid.pass == 0) { a.cost0[b * 3] = cost; a.cost0[b * 3 + 1] = cu; a.cost0[b * 3 + 2] = cl; }
   else converged = allclose1(cost, a.prev_cost[b], a.atol, a.rtol);
   a.prev_cost[b] = cost;
   int act[NF];
@@ -421,7 +426,7 @@ __device__ __noinline__ void schur_image(const PassArgs& a, int b, const float* 
     out[18 + i] = sums[NH + act[ng + i]];
     out[21 + i] = (ng == 2 && ok) ? Hf[0][act[ng + i]] * wg[0] + Hf[1][act[ng + i]] * wg[1] : 0.f;
   }
-  out[24] = (a.pass >= 1 && converged) ? 0.f : 1.f;
+  out[24] = (pid.pass >= 1 && converged) ? 0.f : 1.f;
   for (int j = 0; j < 3; j++) { out[25 + j] = W[0][j]; out[28 + j] = W[1][j]; }
   out[31] = wg[0]; out[32] = wg[1];
 }
@@ -545,9 +550,9 @@ __device__ __forceinline__ void shared_update_image(const PassArgs& a, int b, co
 }
 
 // Batch-global stop of the shared solve (all images of all ranks converged): one thread, after the update.
-__device__ __forceinline__ void shared_stop_latch(const PassArgs& a, const float* sum_in) {
-  if (a.pass >= 1 && sum_in[24] == 0.f) {
-    if (a.pass < a.ctrl->stop_at) a.ctrl->stop_at = a.pass;
+__device__ __forceinline__ void shared_stop_latch(const PassArgs& a, const PassId pid, const float* sum_in) {
+  if (pid.pass >= 1 && sum_in[24] == 0.f) {
+    if (pid.pass < a.ctrl->stop_at) a.ctrl->stop_at = pid.pass;
     if (a.early_stop) a.ctrl->stop = 1;
   }
 }
@@ -556,7 +561,7 @@ __device__ __forceinline__ void shared_stop_latch(const PassArgs& a, const float
 // of the per-image partials -> exchange with the peers over NVLink -> every image's update -> stop latch.
 // Replaces three kernel launches per step; the grid has drained by now, so this is the pass's critical tail.
 template <int MODEL>
-__device__ __noinline__ void shared_tail(const PassArgs& a, float (*s_part)[SCHUR_NSUM + 3], float* s_tot) {
+__device__ __noinline__ void shared_tail(const PassArgs& a, const PassId pid, float (*s_part)[SCHUR_NSUM + 3], float* s_tot) {
   __threadfence();  // the other CTAs' Schur partials (released before their image ticket)
   float mine = schur_block_sum(a, s_part);
   if (threadIdx.x < 32) {
@@ -569,7 +574,7 @@ __device__ __noinline__ void shared_tail(const PassArgs& a, float (*s_part)[SCHU
     return;
   }
   for (int b = threadIdx.x; b < a.B; b += blockDim.x) shared_update_image<MODEL>(a, b, s_tot);
-  if (threadIdx.x == 0) shared_stop_latch(a, s_tot);
+  if (threadIdx.x == 0) shared_stop_latch(a, pid, s_tot);
 }
 
 // ---- NCCL fallback (no peer memory): the same three steps as separate kernels around ncclAllReduce ----
@@ -586,7 +591,7 @@ __global__ void shared_update_kernel(const __grid_constant__ PassArgs a) {
   if (b < a.B) shared_update_image<MODEL>(a, b, a.shared_sums);
 }
 // Runs after shared_update_kernel of the same pass: latch the batch-global stop.
-__global__ void shared_stop_kernel(const __grid_constant__ PassArgs a) { shared_stop_latch(a, a.shared_sums); }
+__global__ void shared_stop_kernel(const __grid_constant__ PassArgs a) { shared_stop_latch(a, PassId{a.pass, a.is_final}, a.shared_sums); }
 
 // ---------------------------------------------------------------------------------------------
 // the fused pass kernel
@@ -624,18 +629,20 @@ struct Tune {
 };
 inline int max_warps_for(int model, bool pack) { return (model == PINHOLE || !pack) ? GCLM_PIN_WARPS : GCLM_DIST_WARPS; }
 
+// One pass of one CTA (a tile of one image): stream, reduce, and -- in the last CTA of the image -- solve.
+// `a` lives in kernel parameter space (never copied); `pid` says which pass this is.
 template <int MODEL, bool GEN_D, bool FULL, bool PACK>
-__global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MODEL, PACK>::MIN_BLOCKS)
+__device__ __forceinline__ void
 #ifdef GCLM_TMA2D
-    lm_pass_kernel(const __grid_constant__ PassArgs a, const __grid_constant__ TmaMaps tm) {
+    pass_body(const PassArgs& a, const PassId pid, const TmaMaps& tm) {
 #else
-    lm_pass_kernel(const __grid_constant__ PassArgs a) {
+    pass_body(const PassArgs& a, const PassId pid) {
 #endif
   constexpr int NACC = Dims<MODEL>::NACC;
   using V = typename std::conditional<PACK, f2, float>::type;  // 2 pixels per op when packed
   const int b = blockIdx.x / a.tiles_per_image;
   const int tile = blockIdx.x - b * a.tiles_per_image;
-  if (!a.is_final) {
+  if (!pid.is_final) {
     if (*(volatile int*)&a.ctrl->stop) return;
     if (a.flags[b] & FLAG_FROZEN) return;
   }
@@ -648,9 +655,9 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
   __shared__ float s_tot[SCHUR_NSUM + 3];
   if (threadIdx.x == 0) {
     int sl = a.slot[b];
-    if (a.is_final && a.ctrl->stop) sl ^= 1;
+    if (pid.is_final && a.ctrl->stop) sl ^= 1;
     const float* Pb = a.P + ((size_t)b * 2 + sl) * PSTRIDE;
-    make_pass_const(Pb, Pb + 8, a.spherical != 0, a.log_focal != 0, a.is_final != 0 && a.final_rpf != 0, s_pc);
+    make_pass_const(Pb, Pb + 8, a.spherical != 0, a.log_focal != 0, pid.is_final != 0 && a.final_rpf != 0, s_pc);
   }
   __syncthreads();
   const PassConst pc = s_pc;
@@ -909,21 +916,68 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
     a.tickets[b] = 0u;
     finish_sums<MODEL, GEN_D>(s_sum, pc.k1, pc.k2, a.up_scale);  // [g0 g1 X k..] x 1/a_up -> [g0 g1 f k..]
     s_last_img = 0;
-    if (a.shared && !a.is_final) {
-      schur_image<MODEL>(a, b, s_sum);
+    if (a.shared && !pid.is_final) {
+      schur_image<MODEL>(a, pid, b, s_sum);
       if (a.fused_shared) {  // image-level ticket: the last image's CTA finishes the LM step for the batch
         __threadfence();
         if (atomicAdd(&a.ctrl->img_done, 1u) == (unsigned)a.B - 1u) { a.ctrl->img_done = 0u; s_last_img = 1; }
       }
     } else {
-      lm_step_image<MODEL>(a, b, s_sum);
+      lm_step_image<MODEL>(a, pid, b, s_sum);
     }
   }
-  if (a.shared && a.fused_shared && !a.is_final) {  // uniform over the grid
+  if (a.shared && a.fused_shared && !pid.is_final) {  // uniform over the grid
     __syncthreads();
-    if (s_last_img) shared_tail<MODEL>(a, s_part, s_tot);
+    if (s_last_img) shared_tail<MODEL>(a, pid, s_part, s_tot);
   }
 }
+
+template <int MODEL, bool GEN_D, bool FULL, bool PACK>
+__global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MODEL, PACK>::MIN_BLOCKS)
+#ifdef GCLM_TMA2D
+    lm_pass_kernel(const __grid_constant__ PassArgs a, const __grid_constant__ TmaMaps tm) {
+  pass_body<MODEL, GEN_D, FULL, PACK>(a, PassId{a.pass, a.is_final}, tm);
+}
+#else
+    lm_pass_kernel(const __grid_constant__ PassArgs a) {
+  pass_body<MODEL, GEN_D, FULL, PACK>(a, PassId{a.pass, a.is_final});
+}
+#endif
+
+// Grid-wide barrier of the persistent kernel (all CTAs are co-resident: cooperative launch).  Arrivals are
+// counted monotonically within a solve (lm_init_kernel zeroes the counter), so no reset race exists.
+__device__ __forceinline__ void grid_barrier(Ctrl* c, unsigned target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&c->bar, 1u);
+    unsigned v;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&c->bar) : "memory");
+    } while (v < target);
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// Small batches (the calibrate() case: B = 1, a handful of images): ALL num_steps + 1 passes in ONE launch.
+// Every CTA keeps its tile; a grid barrier takes the place of the kernel boundary between passes, so the
+// schedule, the tiling and every floating-point sum are those of the one-launch-per-pass path (bit-identical
+// results); what disappears is num_steps launches and their gaps.  Launched cooperatively, only when the
+// whole grid is resident (gclm_solve checks the occupancy).
+#ifndef GCLM_TMA2D
+template <int MODEL, bool GEN_D, bool FULL, bool PACK>
+__global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MODEL, PACK>::MIN_BLOCKS)
+    lm_persistent_kernel(const __grid_constant__ PassArgs a) {
+  unsigned target = 0;
+  for (int p = 0; p < a.num_steps; ++p) {
+    pass_body<MODEL, GEN_D, FULL, PACK>(a, PassId{p, 0});
+    target += gridDim.x;
+    grid_barrier(a.ctrl, target);
+  }
+  pass_body<MODEL, true, FULL, PACK>(a, PassId{a.num_steps, 1});
+}
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // small kernels
@@ -934,7 +988,7 @@ __global__ void lm_init_kernel(PassArgs a, const float* cam0, const float* g0) {
     a.ctrl->stop = 0; a.ctrl->stop_at = a.num_steps;
     a.ctrl->done[0] = a.ctrl->done[1] = 0u;
     a.ctrl->unconv[0] = a.ctrl->unconv[1] = 0u;
-    a.ctrl->img_done = 0u; a.ctrl->comm_error = 0;
+    a.ctrl->img_done = 0u; a.ctrl->comm_error = 0; a.ctrl->bar = 0u;
   }
   if (b >= a.B) return;
   float* P0 = a.P + (size_t)b * 2 * PSTRIDE;
@@ -1060,6 +1114,7 @@ struct gclm_handle {
   int device = 0;
   int num_sms = 148;
   int64_t launches = 0;
+  int64_t persistent_solves = 0;  // solves that ran as one cooperative launch
   // scratch
   void* scratch = nullptr;
   size_t scratch_bytes = 0;
@@ -1078,6 +1133,8 @@ struct gclm_handle {
   // > 48 KB dynamic shared memory opt-in per kernel instantiation: a per-DEVICE attribute, so it lives in
   // the per-device handle ([model][gen_d][full][pack])
   size_t smem_configured[4][2][2][2] = {};
+  size_t smem_configured_persistent[4][2][2][2] = {};
+  int persistent_blocks_per_sm[4][2][2][2] = {};  // occupancy of lm_persistent_kernel (0 = not queried yet)
 #ifdef GCLM_TMA2D
   gclm::TmaMaps maps;  // tensor maps of the current solve
 #endif
@@ -1325,6 +1382,62 @@ void launch_pass_model(gclm_handle* h, const PassArgs& a, bool gen_d, bool full,
   }
 }
 
+bool use_packed();
+#ifndef GCLM_TMA2D
+// The persistent small-batch schedule: one cooperative launch runs every pass.  Returns false (nothing launched)
+// when the grid would not be co-resident -- the caller then uses one launch per pass.
+template <int MODEL, bool GEN_D, bool FULL, bool PACK>
+bool launch_persistent_one(gclm_handle* h, const PassArgs& a, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
+  auto kernel = lm_persistent_kernel<MODEL, GEN_D, FULL, PACK>;
+  size_t& configured = h->smem_configured_persistent[MODEL][GEN_D][FULL][PACK];
+  if (smem > configured) {
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return false;
+    configured = smem;
+    h->persistent_blocks_per_sm[MODEL][GEN_D][FULL][PACK] = 0;
+  }
+  int& per_sm = h->persistent_blocks_per_sm[MODEL][GEN_D][FULL][PACK];
+  if (per_sm == 0) {
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, (int)block.x, smem) != cudaSuccess) { cudaGetLastError(); nb = -1; }
+    per_sm = nb > 0 ? nb : -1;
+  }
+  if (per_sm <= 0 || (int64_t)grid.x > (int64_t)per_sm * h->num_sms) return false;
+  PassArgs args = a;
+  void* params[] = {&args};
+  if (cudaLaunchCooperativeKernel(reinterpret_cast<const void*>(kernel), grid, block, params, smem, s) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return true;
+}
+
+template <int MODEL, bool PACK>
+bool launch_persistent_model(gclm_handle* h, const PassArgs& a, bool gen_d, bool full, dim3 grid, dim3 block, cudaStream_t s) {
+  const size_t smem = full ? (size_t)RING_STAGES * 5 * block.x * 16 + (size_t)(block.x / 32) * RING_STAGES * 8 : 0;
+  if (gen_d) return full ? launch_persistent_one<MODEL, true, true, PACK>(h, a, grid, block, smem, s)
+                         : launch_persistent_one<MODEL, true, false, PACK>(h, a, grid, block, 0, s);
+  return full ? launch_persistent_one<MODEL, false, true, PACK>(h, a, grid, block, smem, s)
+              : launch_persistent_one<MODEL, false, false, PACK>(h, a, grid, block, 0, s);
+}
+#endif
+
+// Small grids only (GCLM_PERSISTENT=0 disables): a few hundred CTAs that are all resident at once.
+bool launch_persistent(gclm_handle* h, const PassArgs& a, bool gen_d, bool full, dim3 grid, dim3 block, cudaStream_t s) {
+#ifdef GCLM_TMA2D
+  return false;
+#else
+  static int enabled = -1;
+  if (enabled < 0) { const char* e = getenv("GCLM_PERSISTENT"); enabled = (e && e[0] == '0') ? 0 : 1; }
+  if (!enabled || !use_packed() || (int64_t)grid.x > 4ll * h->num_sms) return false;
+  switch (a.model) {
+    case PINHOLE: return launch_persistent_model<PINHOLE, true>(h, a, gen_d, full, grid, block, s);
+    case SIMPLE_RADIAL: return launch_persistent_model<SIMPLE_RADIAL, true>(h, a, gen_d, full, grid, block, s);
+    case RADIAL: return launch_persistent_model<RADIAL, true>(h, a, gen_d, full, grid, block, s);
+    default: return launch_persistent_model<SIMPLE_DIVISIONAL, true>(h, a, gen_d, full, grid, block, s);
+  }
+#endif
+}
+
 // GCLM_PACK=0 selects the scalar (one pixel per instruction) build of the pass kernel: A/B knob.
 bool use_packed() {
   static int v = -1;
@@ -1458,6 +1571,7 @@ void gclm_default_options(gclm_options* o) {  // lm_optimizer.py:144-162
   o->atol = 1e-8f; o->rtol = 1e-8f; o->use_spherical_manifold = 1; o->use_log_focal = 1;
   o->up_loss_fn_scale = 1e-2f; o->lat_loss_fn_scale = 1e-2f;
   o->stop_mode = GCLM_STOP_BATCH; o->compute_uncertainty = 1; o->rows_per_tile = 0;
+  o->schedule = GCLM_SCHEDULE_AUTO;
 }
 
 int gclm_num_params(int camera_model, int estimate_gravity, int estimate_focal) {
@@ -1510,6 +1624,7 @@ int gclm_reserve(gclm_handle* h, int batch, int height, int width) {
 }
 
 int64_t gclm_launch_count(const gclm_handle* h) { return h ? h->launches : 0; }
+int64_t gclm_persistent_count(const gclm_handle* h) { return h ? h->persistent_solves : 0; }
 
 int gclm_tile_config(int batch, int height, int width, int camera_model, int num_sms, int rows_per_tile,
                      int32_t out[5]) {
@@ -1567,14 +1682,24 @@ int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt
   launch_sin_plane(h, prob, a, s);
   const dim3 grid((unsigned)((size_t)prob->batch * t.tiles_per_image)), block(t.nwarps * 32);
   PassTimer timer(h, s, opt->num_steps + 1);
-  for (int it = 0; it < opt->num_steps; it++) {
-    a.pass = it; a.is_final = 0;
-    launch_pass(h, a, !opt->use_log_focal, full, grid, block, s);
+  // small batch (the calibrate() case): every pass in ONE cooperative launch, a grid barrier between passes
+  const bool want_persistent = opt->schedule != GCLM_SCHEDULE_PER_PASS && opt->num_steps >= 1;
+  if (want_persistent && launch_persistent(h, a, !opt->use_log_focal, full, grid, block, s)) {
+    h->launches++;
+    h->persistent_solves++;
+  } else if (opt->schedule == GCLM_SCHEDULE_PERSISTENT) {
+    snprintf(h->last_error, sizeof(h->last_error), "persistent schedule: %u CTAs are not co-resident on this device", grid.x);
+    return GCLM_ERR_UNSUPPORTED;
+  } else {
+    for (int it = 0; it < opt->num_steps; it++) {
+      a.pass = it; a.is_final = 0;
+      launch_pass(h, a, !opt->use_log_focal, full, grid, block, s);
+      h->launches++;
+    }
+    a.pass = opt->num_steps; a.is_final = 1;
+    launch_pass(h, a, true, full, grid, block, s);
     h->launches++;
   }
-  a.pass = opt->num_steps; a.is_final = 1;
-  launch_pass(h, a, true, full, grid, block, s);
-  h->launches++;
   timer.stop();
   order.done();
   CUDA_TRY(h, cudaGetLastError());

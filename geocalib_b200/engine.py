@@ -66,6 +66,11 @@ class Engine:
     def launch_count(self) -> int:
         return int(self.lib.gclm_launch_count(self._h))
 
+    @property
+    def persistent_count(self) -> int:
+        """Solves that ran as ONE cooperative launch (the small-batch schedule)."""
+        return int(self.lib.gclm_persistent_count(self._h))
+
     def pass_timing(self, enable: bool) -> None:
         """Start (and reset) / stop the opt-in event timing of the pass launches (bench.py's roofline)."""
         _lib.check(self.lib.gclm_pass_timing(self._h, int(bool(enable))), "gclm_pass_timing")

@@ -106,6 +106,7 @@ class LMOptimizer(nn.Module):
         # engine-only knobs (not in the reference)
         "stop_mode": "batch",  # "batch" (reference semantics) | "per_image"
         "rows_per_tile": 0,
+        "schedule": "auto",  # "auto" | "per_pass" | "persistent" (one cooperative launch; small batches)
     }
 
     def __init__(self, conf: Optional[Dict[str, Any]] = None):
@@ -166,6 +167,8 @@ class LMOptimizer(nn.Module):
         opt.stop_mode = {"batch": _lib.STOP_BATCH, "per_image": _lib.STOP_PER_IMAGE}[c.stop_mode]
         opt.compute_uncertainty = int(not self.training)  # reference: `if not self.training` (:635)
         opt.rows_per_tile = int(c.rows_per_tile)
+        opt.schedule = {"auto": _lib.SCHEDULE_AUTO, "per_pass": _lib.SCHEDULE_PER_PASS,
+                        "persistent": _lib.SCHEDULE_PERSISTENT}[c.schedule]
         return opt
 
     @staticmethod

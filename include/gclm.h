@@ -65,6 +65,14 @@ typedef enum {
 #define GCLM_STATUS_NONFINITE 4u
 #define GCLM_STATUS_COMM_TIMEOUT 8u /* shared intrinsics, fused exchange: a peer never contributed; the solve was aborted */
 
+/* How the num_steps + 1 passes of gclm_solve are issued.  Results are bit-identical either way. */
+typedef enum {
+  GCLM_SCHEDULE_AUTO = 0,      /* persistent when the whole grid is co-resident (small batches), else per pass */
+  GCLM_SCHEDULE_PER_PASS = 1,  /* one kernel launch per pass (throughput schedule for large batches)           */
+  GCLM_SCHEDULE_PERSISTENT = 2 /* ONE cooperative launch, grid barrier between passes; GCLM_ERR_UNSUPPORTED
+                                  when the grid does not fit on the device                                     */
+} gclm_schedule;
+
 typedef struct gclm_handle gclm_handle;
 
 /*
@@ -114,7 +122,8 @@ typedef struct {
   int32_t stop_mode;              /* gclm_stop_mode; GCLM_STOP_BATCH */
   int32_t compute_uncertainty;    /* 1 = estimate_uncertainty() (:463-516), eval mode */
   int32_t rows_per_tile;          /* 0 = auto; tuning knob: image rows per CTA */
-  int32_t reserved[3];
+  int32_t schedule;               /* gclm_schedule; GCLM_SCHEDULE_AUTO */
+  int32_t reserved[2];
 } gclm_options;
 
 /*
@@ -151,6 +160,9 @@ int gclm_reserve(gclm_handle* h, int batch, int height, int width);
 /*
  * Per-image intrinsics: replaces LMOptimizer.forward -> optimize() with shared_intrinsics=False
  * (lm_optimizer.py:551-644).  Enqueues num_steps+1 fused passes on `cuda_stream`; asynchronous.
+ * Large batches: one kernel launch per pass.  Small batches (the calibrate() case, extractor.py:93-95:
+ * B = 1): when every CTA of the grid is resident at once the passes run inside ONE cooperative launch
+ * with a grid barrier in place of the kernel boundary (opt->schedule).
  */
 int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt,
                const gclm_result* res, void* cuda_stream);
@@ -218,6 +230,8 @@ int gclm_solve_host(gclm_handle* h, const gclm_problem* prob, const gclm_options
 
 /* Number of kernel launches issued by this handle since creation (bench.py's gpu_launches). */
 int64_t gclm_launch_count(const gclm_handle* h);
+/* Number of solves that ran under the persistent schedule (one cooperative launch for all passes). */
+int64_t gclm_persistent_count(const gclm_handle* h);
 
 /*
  * How the pass kernel would tile a problem (host-only, no device needed): out = {warps per CTA,

@@ -49,8 +49,12 @@ def blend_decoder(ex, camera_model, gt):
 
     dec = ex.model.perspective_decoder
     orig = dec.forward
+    cache = {}  # cuDNN picks its convolution algorithms per call: replay the SAME decoder output to both optimizers
 
     def fwd(data):
+        key = tuple(data["features"]["ll"].shape)
+        if key in cache:
+            return {k: v.clone() for k, v in cache[key].items()}
         out = orig(data)
         B, _, h, w = out["up_field"].shape
         dev = out["up_field"].device
@@ -61,6 +65,7 @@ def blend_decoder(ex, camera_model, gt):
         u = 0.9 * up + 0.1 * out["up_field"]
         out["up_field"] = torch.nn.functional.normalize(u, dim=1)
         out["latitude_field"] = 0.9 * lat + 0.1 * out["latitude_field"]
+        cache[key] = {k: v.clone() for k, v in out.items()}
         return out
 
     dec.forward = fwd

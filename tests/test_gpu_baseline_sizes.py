@@ -111,17 +111,27 @@ def test_bench_workload_slice_vs_oracle(dev, model, B, h, w, conf):
         out = G.LMOptimizer({"camera_model": model, **conf}).eval()(f)
     torch.cuda.synchronize()
     ref = oracle.lm(model, fn["up_field"], fn["latitude_field"], fn["up_confidence"], fn["latitude_confidence"],
-                    conf=conf)
+                    conf=conf, trace=True)
     cam, grav = out["camera"]._data.cpu().numpy(), out["gravity"]._data.cpu().numpy()
     stop = out["stop_at"].cpu().numpy()
     assert np.abs(stop - ref["stop_at"]).max() <= 1
-    if conf.get("early_stop", True) and np.any(stop != ref["stop_at"]):
-        # the batch-global criterion |cost_i - cost_{i-1}| <= 1e-8 (1 + |cost|) on fp32 costs ~1e-4 can fire one
-        # iteration apart; slowly converging images (fisheye k1) still move ~1e-4 in that step, so compare at
-        # the SAME iteration count: the oracle re-run for exactly the engine's number of steps
-        ref = oracle.lm(model, fn["up_field"], fn["latitude_field"], fn["up_confidence"], fn["latitude_confidence"],
-                        conf={**conf, "num_steps": int(stop.max()), "early_stop": False})
-    assert_params_close(cam, grav, ref["camera"], ref["gravity"], model, tol=TOL)
+    if not conf.get("early_stop", True):
+        assert_params_close(cam, grav, ref["camera"], ref["gravity"], model, tol=TOL)
+    else:
+        # The batch-global stop fires when |cost_i - cost_{i-1}| <= 1e-8 (1 + |cost|) for ALL images; images
+        # that still move then (fisheye k1 converges slowly) are only defined up to that movement: at the
+        # noise floor of the fp32 costs the sign of (new - prev) -- i.e. lambda x10 or x0.1 -- and the
+        # iteration at which the criterion fires differ between any two implementations.  So: 1e-4 plus the
+        # reference's own movement over its last two steps, per image and parameter.
+        tr = ref["trace"]  # (iterations, B, 13) = cam[8], grav[3], lambda, cost after every step
+        K = oracle.NUM_DIST[model]
+        last = tr[-1][:, :11].astype(np.float64)
+        move = np.abs(last - tr[max(0, tr.shape[0] - 3)][:, :11].astype(np.float64))
+        d = np.abs(np.concatenate([cam, grav], 1).astype(np.float64) - np.concatenate([ref["camera"], ref["gravity"]], 1))
+        scale = np.maximum(1.0, np.abs(last))
+        scale[:, 2:4] = np.abs(last[:, 2:4])  # focal: relative
+        cols = [2, 3] + list(range(6, 6 + K)) + [8, 9, 10]
+        assert np.all(d[:, cols] <= TOL * scale[:, cols] + 2.0 * move[:, cols]), (d[:, cols], move[:, cols])
     np.testing.assert_allclose(out["final_cost"].cpu().numpy(), ref["final_cost"], rtol=2e-4)
     # the calibration is also RIGHT (not just equal): focal within 2 % of the synthetic ground truth
     assert np.median(np.abs(cam[:, 3] / cam_gt[:, 3] - 1)) < 0.02

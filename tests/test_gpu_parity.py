@@ -56,6 +56,19 @@ def run_engine_on_golden(g, dev, extra_conf=None, eval_mode=True):
     return out
 
 
+def assert_cov_close(cov, cov_r, tol=1e-3):
+    """Covariance = inverse of the undamped rpf Hessian at the FINAL estimate (lm_optimizer.py:481-484).  It
+    inherits (i) the differences of the final parameters (<= 1e-4, each moving H by the same relative order) and
+    (ii) fp32 summation noise (~2e-6 of the scaled Hessian, measured) amplified by cond(H scaled) <= 60.
+    Measured over all golden cases (tools/cov_tolerance.py, profiles/r2_cov_tolerance.txt): <= 4e-6 in the
+    scale sqrt(cov_ii cov_jj) for 14 cases, 2.3e-4 for the one whose focal itself differs by 3.5e-5
+    (no-confidence fisheye).  Tolerance: 1e-3 scaled -- it used to be 1e-2."""
+    cov, cov_r = np.asarray(cov, np.float64), np.asarray(cov_r, np.float64)
+    sd = np.sqrt(np.abs(np.einsum("bii->bi", cov_r)))
+    err = np.abs(cov - cov_r) / (sd[:, :, None] * sd[:, None, :])
+    assert err.max() <= tol, err.max()
+
+
 def rp_of(vec):
     return oracle.gravity_rp(np.asarray(vec, np.float64))
 
@@ -98,11 +111,10 @@ def test_golden_lm(golden_dir, dev, case):
             np.testing.assert_allclose(out[k].cpu().numpy(), g["out_" + k], rtol=5e-4, atol=1e-9, err_msg=k)
         else:
             assert k not in out
-    np.testing.assert_allclose(out["covariance"].cpu().numpy(), g["out_covariance"], rtol=1e-2,
-                               atol=1e-2 * np.abs(g["out_covariance"]).max())
+    assert_cov_close(out["covariance"].cpu().numpy(), g["out_covariance"])
     for k in ("roll_uncertainty", "pitch_uncertainty", "gravity_uncertainty", "focal_uncertainty",
-              "vfov_uncertainty"):
-        np.testing.assert_allclose(out[k].cpu().numpy(), g["out_" + k], rtol=1e-2, atol=1e-7, err_msg=k)
+              "vfov_uncertainty"):  # sqrt of covariance entries: measured <= 1e-4 relative, typically 1e-7
+        np.testing.assert_allclose(out[k].cpu().numpy(), g["out_" + k], rtol=5e-4, atol=1e-7, err_msg=k)
     assert int(out["status"].sum()) == 0
 
 
@@ -215,8 +227,7 @@ def test_engine_matches_oracle(dev, model, h, w, B):
     np.testing.assert_allclose(out["initial_cost"].cpu().numpy(), ref["initial_cost"], rtol=5e-4)
     # iteration counts may differ by one step at fp32 round-off of the cost comparison
     assert np.abs(out["stop_at"].cpu().numpy() - ref["stop_at"]).max() <= 2
-    np.testing.assert_allclose(out["covariance"].cpu().numpy(), ref["covariance"], rtol=2e-2,
-                               atol=2e-2 * np.abs(ref["covariance"]).max())
+    assert_cov_close(out["covariance"].cpu().numpy(), ref["covariance"], tol=2e-3)
 
 
 @pytest.mark.parametrize("model", ["pinhole", "simple_radial"])
@@ -389,8 +400,7 @@ def test_golden_shared_intrinsics(golden_dir, dev, case):
     assert np.ptp(cam[:, 3]) == 0.0  # one focal for the whole batch
     assert np.abs(out["stop_at"].cpu().numpy() - g["out_stop_at"]).max() <= 1
     np.testing.assert_allclose(out["final_cost"].cpu().numpy(), g["out_final_cost"], rtol=5e-4)
-    np.testing.assert_allclose(out["covariance"].cpu().numpy(), g["out_covariance"], rtol=1e-2,
-                               atol=1e-2 * np.abs(g["out_covariance"]).max())
+    assert_cov_close(out["covariance"].cpu().numpy(), g["out_covariance"])
     for k in (1, 2, 3):
         o = run_engine_on_golden(g, dev, {"num_steps": k, "early_stop": False})
         assert_params_close(o["camera"]._data.cpu().numpy(), o["gravity"]._data.cpu().numpy(),
@@ -695,3 +705,56 @@ def test_pass_timing_brackets_the_pass_launches(dev):
     assert torch.equal(out["camera"]._data, ref["camera"]._data)
     opt(f)
     assert eng.pass_time() == (0.0, 0)
+
+
+@pytest.mark.parametrize("model", MODELS)
+@pytest.mark.parametrize("B,h,w", [(1, 240, 320), (3, 96, 128)])
+def test_persistent_schedule_is_bit_identical_to_per_pass(dev, model, B, h, w):
+    """Small batches (calibrate(): B = 1, extractor.py:93-95) run every pass inside ONE cooperative launch with a
+    grid barrier between passes; tiling, summation order and solver are those of the per-pass schedule."""
+    import geocalib_b200 as G
+    from geocalib_b200.engine import get_engine
+
+    cam, grav = synth_params(model, B, h, w, 77)
+    f = render_on_device(model, cam, grav, h, w, dev, sigma=0.02, seed=5)
+    eng = get_engine(dev)
+    outs = {}
+    for sched, conf in (("per_pass", {}), ("persistent", {}), ("persistent_default_conf", None)):
+        c = {"camera_model": model, "schedule": sched.split("_default")[0] if conf is None else sched}
+        if conf is not None:
+            c |= {"num_steps": 10, "early_stop": False}
+        n0, l0 = eng.persistent_count, eng.launch_count
+        with torch.no_grad():
+            outs[sched] = G.LMOptimizer(c).eval()(f)
+        torch.cuda.synchronize()
+        if sched.startswith("persistent"):
+            assert eng.persistent_count == n0 + 1
+            assert eng.launch_count - l0 == 3  # initial estimate, sin(latitude) plane, the persistent kernel
+        else:
+            assert eng.persistent_count == n0 and eng.launch_count - l0 == 2 + 11
+    a, b = outs["per_pass"], outs["persistent"]
+    for k in ("camera", "gravity"):
+        assert torch.equal(a[k]._data, b[k]._data), k
+    for k in ("covariance", "final_cost", "initial_cost", "stop_at", "focal_uncertainty", "status"):
+        assert torch.equal(a[k], b[k]), k
+    # default configuration (early stop on, 30 steps): the batch-global stop latch works across the grid barrier
+    with torch.no_grad():
+        ref = G.LMOptimizer({"camera_model": model, "schedule": "per_pass"}).eval()(f)
+    d = outs["persistent_default_conf"]
+    assert torch.equal(ref["camera"]._data, d["camera"]._data) and torch.equal(ref["stop_at"], d["stop_at"])
+    assert float(d["stop_at"].max()) < 30  # it did stop early
+
+
+def test_auto_schedule_picks_persistent_only_for_small_grids(dev):
+    import geocalib_b200 as G
+    from geocalib_b200.engine import get_engine
+
+    eng = get_engine(dev)
+    for B, expect in ((2, 1), (700, 0)):
+        cam, grav = synth_params("pinhole", B, 96, 128, 3)
+        f = render_on_device("pinhole", cam, grav, 96, 128, dev, sigma=0.02, seed=1)
+        n0 = eng.persistent_count
+        with torch.no_grad():
+            G.LMOptimizer({"camera_model": "pinhole", "num_steps": 5, "early_stop": False}).eval()(f)
+        torch.cuda.synchronize()
+        assert eng.persistent_count - n0 == expect
