@@ -476,7 +476,8 @@ def time_workload(args, workload, wl, ctx, *, with_e2e, with_parity):
     fields = eng.render_fields(model, torch.from_numpy(cam_gt).to(dev), torch.from_numpy(grav_gt).to(dev), h, w,
                                sigma=0.02, conf_lo=0.2, seed=1234 + rank)
     opt = G.LMOptimizer({"camera_model": model, "num_steps": iters, "early_stop": False,
-                         "rows_per_tile": args.rows_per_tile}).eval()
+                         "rows_per_tile": args.rows_per_tile,
+                         "confidence_dtype": "float16" if args.conf16 and not shared else "float32"}).eval()
     opt.shared_intrinsics = shared
     collective = "none"
     if shared and world > 1:
@@ -534,7 +535,7 @@ def time_workload(args, workload, wl, ctx, *, with_e2e, with_parity):
 
     # ---- roofline of the fused pass kernel ----
     passes = iters + 1
-    bytes_per_launch = B * h * w * BYTES_PER_PIXEL_PASS
+    bytes_per_launch = B * h * w * (16 if args.conf16 and not shared else BYTES_PER_PIXEL_PASS)
     # average duration of one pass launch inside the timed region: CUDA events recorded by the engine on
     # the solve stream around the `passes` back-to-back launches of each timed solve (max over ranks);
     # the once-per-solve set-up kernels (initial estimate, sin plane) are outside the bracket
@@ -546,7 +547,8 @@ def time_workload(args, workload, wl, ctx, *, with_e2e, with_parity):
                 "kernel": "gclm::lm_pass_kernel", "bytes_per_launch": bytes_per_launch,
                 "launch_ms": launch_ms, "passes_per_step": passes, "step_ms_per_pass": ms_per_step / passes,
                 "step_frac": bytes_per_launch * passes / (ms_per_step * 1e-3) / 1e9 / peak,
-                "timed_launches": pass_launches}
+                "timed_launches": pass_launches,
+                "bytes_per_pixel_pass": 16 if args.conf16 and not shared else BYTES_PER_PIXEL_PASS}
 
     # ---- small batches (the calibrate() case): latency of one solve replayed from a CUDA graph ----
     graph = None
@@ -618,6 +620,8 @@ def main():
     ap.add_argument("--no-shared", action="store_true", help="skip the shared-intrinsics sub-record")
     ap.add_argument("--e2e-chunk", type=int, default=128)
     ap.add_argument("--rows-per-tile", type=int, default=0, help="engine tiling knob (0 = auto)")
+    ap.add_argument("--conf16", action="store_true", help="stream the 16 B/pixel layout (sin(lat) + fp16 confidences; "
+                    "packed once per solve inside the timed step): SURVEY 8f.1 experiment, not the headline")
     ap.add_argument("--no-check", action="store_true", help="skip the calibration / parity checks (experiments)")
     args = ap.parse_args()
     wl = list(WORKLOADS[args.workload])

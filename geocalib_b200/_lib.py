@@ -62,6 +62,15 @@ class Result(ctypes.Structure):
     ]
 
 
+class PackedFields(ctypes.Structure):
+    _fields_ = [
+        ("batch", c_int32), ("height", c_int32), ("width", c_int32), ("conf_format", c_int32),
+        ("up", c_void_p), ("sin_lat", c_void_p), ("up_conf", c_void_p), ("lat_conf", c_void_p),
+    ]
+
+
+CONF_F32, CONF_F16 = 0, 1
+
 # every symbol include/gclm.h declares: (restype, argtypes)
 SIGNATURES = {
     "gclm_version": (c_int, []),
@@ -72,6 +81,10 @@ SIGNATURES = {
     "gclm_destroy": (c_int, [c_void_p]),
     "gclm_reserve": (c_int, [c_void_p, c_int, c_int, c_int]),
     "gclm_solve": (c_int, [c_void_p, POINTER(Problem), POINTER(Options), POINTER(Result), c_void_p]),
+    "gclm_solve_packed": (c_int, [c_void_p, POINTER(PackedFields), POINTER(Problem), POINTER(Options), POINTER(Result), c_void_p]),
+    "gclm_pack_fields": (c_int, [c_void_p, POINTER(Problem), c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gclm_pack_decoder_outputs": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
+                                          c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gclm_system": (c_int, [c_void_p, POINTER(Problem), POINTER(Options), c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gclm_solve_shared": (c_int, [c_void_p, POINTER(Problem), POINTER(Options), POINTER(Result), c_void_p, c_void_p]),
     "gclm_comm_unique_id": (c_int, [c_void_p]),

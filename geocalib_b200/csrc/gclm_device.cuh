@@ -333,8 +333,8 @@ GCLM_HD __forceinline__ void model_scalars(const PassConst& pc, V r2, ModelScala
     const V x = fmaf(-4.f * pc.k1, r2, splat<V>(1.f));
     const V xs = fmaxf(x, 1e-6f);
     const V it = fast_rsqrt(xs), t = xs * it, w = 1.f + t, iw = fast_rcp(w);
-    const V g4 = (4.f * it) * iw * iw, it2 = it * it;  // 4 / (t w^2)
     m.s = 2.f * iw;
+    const V g4 = (it * m.s) * m.s, it2 = it * it;  // 4 / (t w^2)
     m.phi = (2.f * pc.k1) * g4; m.A = m.phi;
     m.Bc = (8.f * pc.k1 * pc.k1) * fmaf(3.f, t, splat<V>(1.f)) * g4 * it2 * iw;  // general focal direction only
     m.sk[0] = r2 * g4;
@@ -357,17 +357,23 @@ GCLM_HD __forceinline__ void model_scalars(const PassConst& pc, V r2, ModelScala
 // ------------------------------------------------------------------------------------------
 struct FieldMask { bool up, lat, up_conf, lat_conf; };
 
-// A/B knobs (profiles/r2_ab_*.txt).  Pinhole sits at the 128-register cap of its 2 x 8-warp CTA shape: keeping
-// the column-invariant terms live across the row loop costs it more in register moves than the FMAs it saves
-// (0.97 -> 0.92 of the roofline), so by default only the distortion models (168 registers) use those forms.
+// A/B knobs, measured on B200 (profiles/r2_ab_forms.txt; ncu source view: every packed fp32x2 instruction --
+// FFMA2, FMUL2 or FADD2 -- costs the same two FMA-pipe cycles, so only the NUMBER of packed instructions and
+// the register pressure matter, not which of the three they are):
+//   * pinhole sits at the 128-register cap of its 2 x 8-warp CTA shape and at 0.89-0.97 of the HBM roofline:
+//     neither the column-invariant forms (register moves: 0.97 -> 0.92) nor the scale-folded Huber form
+//     (-1 %) pay, so it keeps the round-1 formulas;
+//   * the distortion models take the X basis and the folded Huber form (fewer packed instructions);
+//     trading FMAs for hoisted products + adds (COLS) leaves the instruction count unchanged and costs
+//     registers: off by default (0.661 vs 0.652 of the roofline on simple_radial at equal clocks).
 #ifndef GCLM_PIN_GEOM_NEW
 #define GCLM_PIN_GEOM_NEW 0
 #endif
 #ifndef GCLM_PIN_HUBER_NEW
-#define GCLM_PIN_HUBER_NEW 1
+#define GCLM_PIN_HUBER_NEW 0
 #endif
 #ifndef GCLM_DIST_COLS
-#define GCLM_DIST_COLS 1
+#define GCLM_DIST_COLS 0
 #endif
 template <int MODEL> struct Forms {
   static constexpr bool COLS = MODEL != PINHOLE ? GCLM_DIST_COLS != 0 : GCLM_PIN_GEOM_NEW != 0;  // column-invariant forms (LICM food)
@@ -682,7 +688,11 @@ template <int MODEL, bool GEN_D, bool FULL, bool PACK>
 GCLM_HD __forceinline__ void row_accumulate(const PassConst& pc, const FieldMask fm, const RowCols<PACK>& cols, float v,
                                             const float4 ox, const float4 oy, const float4 ol, const float4 cu,
                                             const float4 cl, const RobustConst& rc,
-                                            typename std::conditional<PACK, f2, float>::type (&acc)[Dims<MODEL>::NACC]) {
+                                            typename std::conditional<PACK, f2, float>::type (&acc)[Dims<MODEL>::NACC],
+                                            const PassConst* pc_mem = nullptr, const RobustConst* rc_mem = nullptr) {
+  // pc_mem / rc_mem: the constants where they live in (shared) memory -- handed to the noinline cold path so
+  // that the register copies `pc` / `rc` never have their address taken (a per-thread local-memory copy
+  // otherwise: 110 B x threads of DRAM writes per launch, seen in ncu)
   constexpr int NACC = Dims<MODEL>::NACC;
   using V = typename std::conditional<PACK, f2, float>::type;
   const float sl0 = ol.x, sl1 = ol.y, sl2 = ol.z, sl3 = ol.w;
@@ -712,8 +722,10 @@ GCLM_HD __forceinline__ void row_accumulate(const PassConst& pc, const FieldMask
 #pragma unroll 1
         for (int i = 0; i < 4; i++) {
           // the k1 == 0 literal path yields the f column directly; X == f there (kappa = 0)
-          if (cold[i]) pixel_scalar<MODEL, GEN_D, FULL, true>(pc, fm, us[i], v, oxs[i], oys[i], sls[i], cus[i], cls[i], rc, d);
-          else pixel_scalar<MODEL, GEN_D, FULL, false>(pc, fm, us[i], v, oxs[i], oys[i], sls[i], cus[i], cls[i], rc, d);
+          const PassConst& pcm = pc_mem ? *pc_mem : pc;
+          const RobustConst& rcm = rc_mem ? *rc_mem : rc;
+          if (cold[i]) pixel_scalar<MODEL, GEN_D, FULL, true>(pcm, fm, us[i], v, oxs[i], oys[i], sls[i], cus[i], cls[i], rcm, d);
+          else pixel_scalar<MODEL, GEN_D, FULL, false>(pcm, fm, us[i], v, oxs[i], oys[i], sls[i], cus[i], cls[i], rcm, d);
 #pragma unroll
           for (int k = 0; k < NACC; k++) acc[k] = acc[k] + splat<V>(share * d[k]);
         }
@@ -766,6 +778,43 @@ GCLM_HD inline void cholesky_solve(const float* L, int n, float* b) {
     b[i] = s / L[i * n + i];
   }
 }
+// The same factorisation and substitution with a compile-time size: fully unrolled, everything in registers
+// (the runtime-n versions above index local-memory arrays).  Same operations in the same order -> same bits.
+template <int N>
+GCLM_HD __forceinline__ bool cholesky_solve_fixed(float (&A)[N][N], float (&b)[N]) {
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    float d = A[j][j];
+#pragma unroll
+    for (int k = 0; k < j; k++) d -= A[j][k] * A[j][k];
+    if (!(d > 0.f)) return false;
+    d = sqrtf(d);
+    A[j][j] = d;
+#pragma unroll
+    for (int i = j + 1; i < N; i++) {
+      float t = A[i][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) t -= A[i][k] * A[j][k];
+      A[i][j] = t / d;
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    float t = b[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) t -= A[i][k] * b[k];
+    b[i] = t / A[i][i];
+  }
+#pragma unroll
+  for (int i = N - 1; i >= 0; i--) {
+    float t = b[i];
+#pragma unroll
+    for (int k = i + 1; k < N; k++) t -= A[k][i] * b[k];
+    b[i] = t / A[i][i];
+  }
+  return true;
+}
+
 // Gauss-Jordan inverse with partial pivoting (torch.inverse, lm_optimizer.py:484).
 GCLM_HD inline bool invert(const float* A, int n, float* Ainv) {
   float a[MAX_NF][2 * MAX_NF];
@@ -816,9 +865,8 @@ GCLM_HD inline void gravity_update(float g[3], float d0, float d1, bool spherica
 GCLM_HD inline void focal_update(float cam[8], float delta, bool as_log) {  // camera.py:136-152
   const float h = cam[1];
   float fy = as_log ? expf(logf(cam[3]) + delta) : cam[3] + delta;
-  const float pi = 3.14159265358979323846f;
-  const float min_f = h / 2.f / tanf((150.f / 180.f * pi) / 2.f);  // vfov 150 deg
-  const float max_f = h / 2.f / tanf((5.f / 180.f * pi) / 2.f);    // vfov 5 deg
+  const float min_f = h / 2.f / 3.7320508075688776f;   // vfov 150 deg: tan(75 deg)
+  const float max_f = h / 2.f / 0.04366094290851206f;  // vfov 5 deg: tan(2.5 deg)
   fy = fminf(fmaxf(fy, min_f), max_f);
   const float fx = fy * cam[2] / cam[3];
   cam[2] = fx; cam[3] = fy;

@@ -16,6 +16,7 @@
 //
 // Passes per solve: num_steps + 1 (the reference makes 2*num_steps + 2 logical passes).
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <stdint.h>
@@ -85,6 +86,7 @@ struct PassArgs {
   int Wt;               // true image width (cost normalisation)
   int rows_per_tile, tiles_per_image, rsub;
   int pass, is_final, shared;
+  int conf16;           // uconf / lconf point at fp16 planes and `lat` already holds sin(latitude) (gclm_solve_packed)
   int model, num_steps, early_stop, fix_lambda, spherical, log_focal, stop_mode;
   int est_gravity, est_focal, est_dist, compute_unc;
   float lambda0, atol, rtol, up_scale, lat_scale;
@@ -129,6 +131,9 @@ __device__ __forceinline__ void cp_async16(unsigned dst_smem, const float* src) 
   asm volatile("cp.async.cg.shared.global.L2::256B [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
 #endif
 }
+__device__ __forceinline__ void cp_async8(unsigned dst_smem, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst_smem), "l"(src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // ---- TMA bulk copy (cp.async.bulk, SASS UBLKCP) + mbarrier helpers (GCLM_TMA build) ----
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -169,6 +174,15 @@ __device__ __forceinline__ float4 lds128(unsigned addr) {
   float4 r;
   asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(addr) : "memory");
   return r;
+}
+
+// four fp16 confidences (8 bytes of shared memory) -> float4
+__device__ __forceinline__ float4 lds_half4(unsigned addr) {
+  unsigned lo, hi;
+  asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(lo), "=r"(hi) : "r"(addr) : "memory");
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&lo));
+  const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&hi));
+  return make_float4(a.x, a.y, b.x, b.y);
 }
 
 __device__ __forceinline__ int active_columns(int model, int est_gravity, int est_focal, int* act) {
@@ -330,14 +344,32 @@ __device__ __noinline__ void lm_step_image(const PassArgs& a, const PassId pid, 
     for (int i = 0; i < NF; i++)
       for (int j = i; j < NF; j++) { Hf[i][j] = sums[idx]; Hf[j][i] = sums[idx]; idx++; }
   }
-  float A[MAX_NF * MAX_NF], d[MAX_NF];
-  for (int i = 0; i < n; i++) {
-    d[i] = sums[NH + act[i]];
-    for (int j = 0; j < n; j++) A[i * n + j] = Hf[act[i]][act[j]];
+  float d[MAX_NF];
+  bool solved;
+  if (n == NF) {  // every block is free (the common case): compile-time size, all in registers
+    float Af[NF][NF], df[NF];
+#pragma unroll
+    for (int i = 0; i < NF; i++) {
+      df[i] = sums[NH + i];
+#pragma unroll
+      for (int j = 0; j < NF; j++) Af[i][j] = Hf[i][j];
+    }
+#pragma unroll
+    for (int i = 0; i < NF; i++) Af[i][i] += fmaxf(Af[i][i] * lam, 1e-6f);
+    solved = cholesky_solve_fixed<NF>(Af, df);
+#pragma unroll
+    for (int i = 0; i < NF; i++) d[i] = df[i];
+  } else {
+    float A[MAX_NF * MAX_NF];
+    for (int i = 0; i < n; i++) {
+      d[i] = sums[NH + act[i]];
+      for (int j = 0; j < n; j++) A[i * n + j] = Hf[act[i]][act[j]];
+    }
+    for (int i = 0; i < n; i++) A[i * n + i] += fmaxf(A[i * n + i] * lam, 1e-6f);
+    solved = cholesky(A, n);
+    if (solved) cholesky_solve(A, n, d);
   }
-  for (int i = 0; i < n; i++) A[i * n + i] += fmaxf(A[i * n + i] * lam, 1e-6f);
-  if (cholesky(A, n)) cholesky_solve(A, n, d);
-  else {
+  if (!solved) {
     for (int i = 0; i < n; i++) d[i] = 0.f;
     a.flags[b] |= GCLM_STATUS_CHOLESKY_FAILED;
   }
@@ -631,12 +663,18 @@ inline int max_warps_for(int model, bool pack) { return (model == PINHOLE || !pa
 
 // One pass of one CTA (a tile of one image): stream, reduce, and -- in the last CTA of the image -- solve.
 // `a` lives in kernel parameter space (never copied); `pid` says which pass this is.
-template <int MODEL, bool GEN_D, bool FULL, bool PACK>
+// IN: how the inputs arrive -- 0 = any subset of the planes (direct 128-bit loads), 1 = all five fp32 planes
+// (cp.async ring), 2 = pre-transformed fields with fp16 confidences (16 B/pixel: gclm_solve_packed).
+template <int MODEL, bool GEN_D, int IN, bool PACK>
 __device__ __forceinline__ void
 #ifdef GCLM_TMA2D
     pass_body(const PassArgs& a, const PassId pid, const TmaMaps& tm) {
 #else
     pass_body(const PassArgs& a, const PassId pid) {
+#endif
+  constexpr bool FULL = IN != 0, C16 = IN == 2;
+#if defined(GCLM_TMA) || defined(GCLM_TMA2D)
+  static_assert(!C16, "fp16 confidences: default cp.async ring only");
 #endif
   constexpr int NACC = Dims<MODEL>::NACC;
   using V = typename std::conditional<PACK, f2, float>::type;  // 2 pixels per op when packed
@@ -647,6 +685,7 @@ __device__ __forceinline__ void
     if (a.flags[b] & FLAG_FROZEN) return;
   }
   __shared__ PassConst s_pc;
+  __shared__ RobustConst s_rc;
   __shared__ float s_red[MAX_WARPS][NACC];
   __shared__ float s_sum[NACC];
   __shared__ int s_last;
@@ -658,11 +697,12 @@ __device__ __forceinline__ void
     if (pid.is_final && a.ctrl->stop) sl ^= 1;
     const float* Pb = a.P + ((size_t)b * 2 + sl) * PSTRIDE;
     make_pass_const(Pb, Pb + 8, a.spherical != 0, a.log_focal != 0, pid.is_final != 0 && a.final_rpf != 0, s_pc);
+    s_rc = make_robust_const(a.up_scale, a.lat_scale);
   }
   __syncthreads();
   const PassConst pc = s_pc;
   const FieldMask fm = {a.up != nullptr, a.lat != nullptr, a.uconf != nullptr, a.lconf != nullptr};
-  const RobustConst rc = make_robust_const(a.up_scale, a.lat_scale);
+  const RobustConst rc = s_rc;
 
   extern __shared__ __align__(16) unsigned char dyn_smem[];
 #ifdef GCLM_TMA2D
@@ -725,8 +765,11 @@ __device__ __forceinline__ void
     const size_t off = (size_t)y0 * W + x0;
     const float* p_ux = (FULL || fm.up) ? a.up + (size_t)b * 2 * N + off : nullptr;
     const float* p_lat = (FULL || fm.lat) ? a.lat + (size_t)b * N + off : nullptr;
-    const float* p_cu = (FULL || fm.up_conf) ? a.uconf + (size_t)b * N + off : nullptr;
-    const float* p_cl = (FULL || fm.lat_conf) ? a.lconf + (size_t)b * N + off : nullptr;
+    // fp16 confidences: the same plane walk in units of half (4 pixels = 8 bytes per lane and row)
+    const float* p_cu = C16 ? nullptr : ((FULL || fm.up_conf) ? a.uconf + (size_t)b * N + off : nullptr);
+    const float* p_cl = C16 ? nullptr : ((FULL || fm.lat_conf) ? a.lconf + (size_t)b * N + off : nullptr);
+    const __half* h_cu = C16 ? reinterpret_cast<const __half*>(a.uconf) + (size_t)b * N + off : nullptr;
+    const __half* h_cl = C16 ? reinterpret_cast<const __half*>(a.lconf) + (size_t)b * N + off : nullptr;
     auto row = [&](const float4 ox, const float4 oy, const float4 ol, const float4 cu, const float4 cl, int y) {
 #ifdef GCLM_NOCOMPUTE  // experiment: pure streaming ceiling of this access pattern
       acc[0] = acc[0] + splat<V>(ox.x + ox.y + ox.z + ox.w + oy.x + oy.y + oy.z + oy.w + ol.x + ol.y + ol.z + ol.w +
@@ -735,9 +778,9 @@ __device__ __forceinline__ void
 #endif
       // `ol` already holds target_lat = sin(latitude_field): sin_plane_kernel ran once before pass 0
 #ifdef GCLM_HOIST
-      row_accumulate<MODEL, GEN_D, FULL, PACK>(pc, fm, cols, pixel_v(pc, y), ox, oy, ol, cu, cl, rc, acc);
+      row_accumulate<MODEL, GEN_D, FULL, PACK>(pc, fm, cols, pixel_v(pc, y), ox, oy, ol, cu, cl, rc, acc, &s_pc, &s_rc);
 #else
-      row_accumulate<MODEL, GEN_D, FULL, PACK>(pc, fm, make_row_cols<PACK>(pc, u), pixel_v(pc, y), ox, oy, ol, cu, cl, rc, acc);
+      row_accumulate<MODEL, GEN_D, FULL, PACK>(pc, fm, make_row_cols<PACK>(pc, u), pixel_v(pc, y), ox, oy, ol, cu, cl, rc, acc, &s_pc, &s_rc);
 #endif
     };
 #ifdef GCLM_TMA2D
@@ -835,14 +878,24 @@ __device__ __forceinline__ void
       // STAGES rows ahead into a private shared-memory slot (no barriers: a lane only ever reads
       // what it copied), so STAGES - 1 rows of loads are in flight while a row is computed and no
       // registers are held across the HBM latency.
-      const unsigned plane_stride = blockDim.x * 16u, stage_stride = 5u * plane_stride;
-      const unsigned slot0 = smem_u32 + threadIdx.x * 16u;  // [stage][plane][thread] x 16 B
+      // slot layout per stage: [up_x | up_y | sin_lat] x 16 B per thread, then the two confidence planes
+      // x 16 B (fp32) or 8 B (fp16) per thread
+      const unsigned plane_stride = blockDim.x * 16u, conf_stride = C16 ? blockDim.x * 8u : plane_stride;
+      const unsigned stage_stride = 3u * plane_stride + 2u * conf_stride;
+      const unsigned slot0 = smem_u32 + threadIdx.x * 16u;  // [stage][plane][thread]
       const unsigned slot_end = slot0 + (unsigned)RING_STAGES * stage_stride;
+      const unsigned conf_off = 3u * plane_stride - (C16 ? threadIdx.x * 8u : 0u);  // from a thread's 16-B slot
       auto issue = [&](unsigned d) {
         cp_async16(d, p_ux); cp_async16(d + plane_stride, p_ux + N);
         cp_async16(d + 2u * plane_stride, p_lat);
-        cp_async16(d + 3u * plane_stride, p_cu); cp_async16(d + 4u * plane_stride, p_cl);
-        p_ux += W; p_lat += W; p_cu += W; p_cl += W;
+        if constexpr (C16) {
+          cp_async8(d + conf_off, h_cu); cp_async8(d + conf_off + conf_stride, h_cl);
+          h_cu += W; h_cl += W;
+        } else {
+          cp_async16(d + 3u * plane_stride, p_cu); cp_async16(d + 4u * plane_stride, p_cl);
+          p_cu += W; p_cl += W;
+        }
+        p_ux += W; p_lat += W;
       };
 #pragma unroll
       for (int st = 0; st < RING_STAGES; st++) {
@@ -854,7 +907,9 @@ __device__ __forceinline__ void
       for (int y = y0; y < y1; ++y) {
         asm volatile("cp.async.wait_group %0;" ::"n"(RING_STAGES > 0 ? RING_STAGES - 1 : 0) : "memory");
         const float4 ox = lds128(d), oy = lds128(d + plane_stride), ol = lds128(d + 2u * plane_stride);
-        const float4 cu = lds128(d + 3u * plane_stride), cl = lds128(d + 4u * plane_stride);
+        float4 cu, cl;
+        if constexpr (C16) { cu = lds_half4(d + conf_off); cl = lds_half4(d + conf_off + conf_stride); }
+        else { cu = lds128(d + 3u * plane_stride); cl = lds128(d + 4u * plane_stride); }
         row(ox, oy, ol, cu, cl, y);
         if (y + RING_STAGES < y1) issue(d);  // refill the slot just consumed (after its values were used)
         cp_async_commit();
@@ -932,15 +987,15 @@ __device__ __forceinline__ void
   }
 }
 
-template <int MODEL, bool GEN_D, bool FULL, bool PACK>
+template <int MODEL, bool GEN_D, int IN, bool PACK>
 __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MODEL, PACK>::MIN_BLOCKS)
 #ifdef GCLM_TMA2D
     lm_pass_kernel(const __grid_constant__ PassArgs a, const __grid_constant__ TmaMaps tm) {
-  pass_body<MODEL, GEN_D, FULL, PACK>(a, PassId{a.pass, a.is_final}, tm);
+  pass_body<MODEL, GEN_D, IN, PACK>(a, PassId{a.pass, a.is_final}, tm);
 }
 #else
     lm_pass_kernel(const __grid_constant__ PassArgs a) {
-  pass_body<MODEL, GEN_D, FULL, PACK>(a, PassId{a.pass, a.is_final});
+  pass_body<MODEL, GEN_D, IN, PACK>(a, PassId{a.pass, a.is_final});
 }
 #endif
 
@@ -971,11 +1026,11 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
     lm_persistent_kernel(const __grid_constant__ PassArgs a) {
   unsigned target = 0;
   for (int p = 0; p < a.num_steps; ++p) {
-    pass_body<MODEL, GEN_D, FULL, PACK>(a, PassId{p, 0});
+    pass_body<MODEL, GEN_D, FULL ? 1 : 0, PACK>(a, PassId{p, 0});
     target += gridDim.x;
     grid_barrier(a.ctrl, target);
   }
-  pass_body<MODEL, true, FULL, PACK>(a, PassId{a.num_steps, 1});
+  pass_body<MODEL, true, FULL ? 1 : 0, PACK>(a, PassId{a.num_steps, 1});
 }
 #endif
 
@@ -1039,6 +1094,59 @@ __global__ void __launch_bounds__(256) repack_kernel(int B, int H, int W, int Wp
     o_sinlat[b * Np + dst] = (in && lat) ? sinf(lat[src]) : 0.f;
     o_uconf[b * Np + dst] = (in && up) ? (uconf ? uconf[src] : 1.f) : 0.f;
     o_lconf[b * Np + dst] = (in && lat) ? (lconf ? lconf[src] : 1.f) : 0.f;
+  }
+}
+
+// ---- pre-transformed field layout: [up_x, up_y, sin_lat, w_up, w_lat], confidences fp32 or fp16 ----
+__device__ __forceinline__ void store_conf4(void* base, size_t i4, float4 c, bool f16) {
+  if (f16) {
+    const __half2 a = __floats2half2_rn(c.x, c.y), b = __floats2half2_rn(c.z, c.w);
+    uint2 u;
+    u.x = *reinterpret_cast<const unsigned*>(&a); u.y = *reinterpret_cast<const unsigned*>(&b);
+    reinterpret_cast<uint2*>(base)[i4] = u;
+  } else {
+    reinterpret_cast<float4*>(base)[i4] = c;
+  }
+}
+// From the five activated planes the CNN heads write today (geocalib.py:44-89): sin(latitude) and the
+// confidences in the requested format; the up planes are already what the pass kernel reads.
+__global__ void __launch_bounds__(256) pack_fields_kernel(size_t n4, const float4* __restrict__ lat, const float4* __restrict__ uconf,
+                                                          const float4* __restrict__ lconf, float4* __restrict__ sin_lat,
+                                                          void* __restrict__ uc_out, void* __restrict__ lc_out, int f16) {
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 x = lat[i];
+    x.x = sinf(x.x); x.y = sinf(x.y); x.z = sinf(x.z); x.w = sinf(x.w);
+    sin_lat[i] = x;
+    store_conf4(uc_out, i, uconf ? uconf[i] : one, f16 != 0);
+    store_conf4(lc_out, i, lconf ? lconf[i] : one, f16 != 0);
+  }
+}
+// The decoder tail fused into the layout the engine streams (geocalib.py:57,73-75,86-88): from the heads'
+// PRE-activation outputs -- F.normalize(up), sin(asin(clamp(tanh(l)))) = clamp(tanh(l)), sigmoid(conf) --
+// written once; no asin/sin round trip, no separate sin plane, optionally half the confidence bytes.
+__global__ void __launch_bounds__(256) pack_decoder_kernel(int B, size_t n4_img, const float4* __restrict__ up_logits,
+                                                           const float4* __restrict__ lat_logits, const float4* __restrict__ ucl,
+                                                           const float4* __restrict__ lcl, float4* __restrict__ up,
+                                                           float4* __restrict__ sin_lat, void* __restrict__ uc_out,
+                                                           void* __restrict__ lc_out, int f16) {
+  const size_t total = (size_t)B * n4_img;
+  auto sig = [](float x) { return 1.f / (1.f + __expf(-x)); };
+  auto tl = [](float x) { return fminf(fmaxf(tanhf(x), -1.f + 1e-5f), 1.f - 1e-5f); };
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / n4_img, j = i - b * n4_img;
+    const float4 x = up_logits[(b * 2) * n4_img + j], y = up_logits[(b * 2 + 1) * n4_img + j];
+    float4 ox, oy;
+    { const float n = fmaxf(sqrtf(x.x * x.x + y.x * y.x), 1e-12f); ox.x = x.x / n; oy.x = y.x / n; }
+    { const float n = fmaxf(sqrtf(x.y * x.y + y.y * y.y), 1e-12f); ox.y = x.y / n; oy.y = y.y / n; }
+    { const float n = fmaxf(sqrtf(x.z * x.z + y.z * y.z), 1e-12f); ox.z = x.z / n; oy.z = y.z / n; }
+    { const float n = fmaxf(sqrtf(x.w * x.w + y.w * y.w), 1e-12f); ox.w = x.w / n; oy.w = y.w / n; }
+    up[(b * 2) * n4_img + j] = ox; up[(b * 2 + 1) * n4_img + j] = oy;
+    const float4 l = lat_logits[i];
+    sin_lat[i] = make_float4(tl(l.x), tl(l.y), tl(l.z), tl(l.w));
+    const float4 cu = ucl[i], cl = lcl[i];
+    store_conf4(uc_out, i, make_float4(sig(cu.x), sig(cu.y), sig(cu.z), sig(cu.w)), f16 != 0);
+    store_conf4(lc_out, i, make_float4(sig(cl.x), sig(cl.y), sig(cl.z), sig(cl.w)), f16 != 0);
   }
 }
 
@@ -1132,7 +1240,7 @@ struct gclm_handle {
   bool have_last = false;
   // > 48 KB dynamic shared memory opt-in per kernel instantiation: a per-DEVICE attribute, so it lives in
   // the per-device handle ([model][gen_d][full][pack])
-  size_t smem_configured[4][2][2][2] = {};
+  size_t smem_configured[4][2][3][2] = {};
   size_t smem_configured_persistent[4][2][2][2] = {};
   int persistent_blocks_per_sm[4][2][2][2] = {};  // occupancy of lm_persistent_kernel (0 = not queried yet)
 #ifdef GCLM_TMA2D
@@ -1351,17 +1459,17 @@ bool encode_maps(gclm_handle* h, const PassArgs& a) {
 }
 #endif
 
-template <int MODEL, bool GEN_D, bool FULL, bool PACK>
+template <int MODEL, bool GEN_D, int IN, bool PACK>
 void launch_one(gclm_handle* h, const PassArgs& a, dim3 grid, dim3 block, size_t smem, cudaStream_t s) {
-  size_t& configured = h->smem_configured[MODEL][GEN_D][FULL][PACK];  // per device (the handle's)
+  size_t& configured = h->smem_configured[MODEL][GEN_D][IN][PACK];  // per device (the handle's)
   if (smem > configured) {
-    cudaFuncSetAttribute(lm_pass_kernel<MODEL, GEN_D, FULL, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaFuncSetAttribute(lm_pass_kernel<MODEL, GEN_D, IN, PACK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = smem;
   }
 #ifdef GCLM_TMA2D
-  lm_pass_kernel<MODEL, GEN_D, FULL, PACK><<<grid, block, smem, s>>>(a, h->maps);
+  lm_pass_kernel<MODEL, GEN_D, IN, PACK><<<grid, block, smem, s>>>(a, h->maps);
 #else
-  lm_pass_kernel<MODEL, GEN_D, FULL, PACK><<<grid, block, smem, s>>>(a);
+  lm_pass_kernel<MODEL, GEN_D, IN, PACK><<<grid, block, smem, s>>>(a);
 #endif
 }
 
@@ -1372,13 +1480,21 @@ void launch_pass_model(gclm_handle* h, const PassArgs& a, bool gen_d, bool full,
   if (full && !encode_maps(h, a)) return;  // leaves the sticky error for cudaGetLastError-less callers: results stay unset
 #else
   const size_t smem = full ? (size_t)RING_STAGES * 5 * block.x * 16 + (size_t)(block.x / 32) * RING_STAGES * 8 : 0;
+  if (a.conf16) {  // pre-transformed fields with fp16 confidences: 3 x 16 B + 2 x 8 B per thread and stage
+    if constexpr (PACK) {
+      const size_t smem16 = (size_t)RING_STAGES * block.x * (3 * 16 + 2 * 8);
+      if (gen_d) launch_one<MODEL, true, 2, PACK>(h, a, grid, block, smem16, s);
+      else launch_one<MODEL, false, 2, PACK>(h, a, grid, block, smem16, s);
+    }
+    return;
+  }
 #endif
   if (gen_d) {
-    if (full) launch_one<MODEL, true, true, PACK>(h, a, grid, block, smem, s);
-    else launch_one<MODEL, true, false, PACK>(h, a, grid, block, 0, s);
+    if (full) launch_one<MODEL, true, 1, PACK>(h, a, grid, block, smem, s);
+    else launch_one<MODEL, true, 0, PACK>(h, a, grid, block, 0, s);
   } else {
-    if (full) launch_one<MODEL, false, true, PACK>(h, a, grid, block, smem, s);
-    else launch_one<MODEL, false, false, PACK>(h, a, grid, block, 0, s);
+    if (full) launch_one<MODEL, false, 1, PACK>(h, a, grid, block, smem, s);
+    else launch_one<MODEL, false, 0, PACK>(h, a, grid, block, 0, s);
   }
 }
 
@@ -1428,7 +1544,7 @@ bool launch_persistent(gclm_handle* h, const PassArgs& a, bool gen_d, bool full,
 #else
   static int enabled = -1;
   if (enabled < 0) { const char* e = getenv("GCLM_PERSISTENT"); enabled = (e && e[0] == '0') ? 0 : 1; }
-  if (!enabled || !use_packed() || (int64_t)grid.x > 4ll * h->num_sms) return false;
+  if (!enabled || !use_packed() || a.conf16 || (int64_t)grid.x > 4ll * h->num_sms) return false;
   switch (a.model) {
     case PINHOLE: return launch_persistent_model<PINHOLE, true>(h, a, gen_d, full, grid, block, s);
     case SIMPLE_RADIAL: return launch_persistent_model<SIMPLE_RADIAL, true>(h, a, gen_d, full, grid, block, s);
@@ -1463,11 +1579,11 @@ void launch_pass(gclm_handle* h, const PassArgs& a, bool gen_d, bool full, dim3 
   }
 }
 
-int validate(const gclm_problem* p, const gclm_options* o) {
+int validate(const gclm_problem* p, const gclm_options* o, bool packed = false) {
   if (!p || !o) return GCLM_ERR_INVALID_ARGUMENT;
   if (p->batch <= 0 || p->height <= 0 || p->width <= 0) return GCLM_ERR_INVALID_ARGUMENT;
   if (p->camera_model < 0 || p->camera_model > 3) return GCLM_ERR_INVALID_ARGUMENT;  // :179-181
-  if (!p->up_field && !p->latitude_field) return GCLM_ERR_INVALID_ARGUMENT;
+  if (!packed && !p->up_field && !p->latitude_field) return GCLM_ERR_INVALID_ARGUMENT;
   if (!p->camera_init || !p->gravity_init) return GCLM_ERR_INVALID_ARGUMENT;
   if (o->num_steps < 0 || o->num_steps > 10000) return GCLM_ERR_INVALID_ARGUMENT;
   if (gclm_num_params(p->camera_model, p->estimate_gravity, p->estimate_focal) <= 0)
@@ -1483,10 +1599,10 @@ bool needs_repack(const gclm_problem* p) {
 inline int padded_width(int w) { return (w + 3) & ~3; }
 
 PassArgs make_args(gclm_handle* h, const gclm_problem* p, const gclm_options* o, const gclm_result* r,
-                   const TileCfg& t, const Layout& L) {
+                   const TileCfg& t, const Layout& L, const gclm_packed_fields* packed = nullptr) {
   PassArgs a;
   memset(&a, 0, sizeof(a));
-  const bool rp = needs_repack(p);
+  const bool rp = !packed && needs_repack(p);
   const int Wp = padded_width(p->width);
   char* sb = static_cast<char*>(h->scratch);
   if (rp) {  // all five planes live in scratch with pitch Wp (repack_kernel)
@@ -1494,6 +1610,10 @@ PassArgs make_args(gclm_handle* h, const gclm_problem* p, const gclm_options* o,
     float* r = reinterpret_cast<float*>(sb + L.repack);
     a.up = r; a.uconf = r + 2 * plane; a.lconf = r + 3 * plane;
     a.lat = reinterpret_cast<const float*>(sb + L.sinlat);
+  } else if (packed) {  // pre-transformed fields: streamed as they are
+    a.up = packed->up; a.lat = packed->sin_lat;
+    a.uconf = static_cast<const float*>(packed->up_conf); a.lconf = static_cast<const float*>(packed->lat_conf);
+    a.conf16 = packed->conf_format == GCLM_CONF_F16;
   } else {
     a.up = p->up_field;
     a.lat = p->latitude_field ? reinterpret_cast<const float*>(sb + L.sinlat) : nullptr;
@@ -1659,10 +1779,10 @@ int gclm_pass_time(gclm_handle* h, double* total_ms, int64_t* passes) {
   return GCLM_OK;
 }
 
-int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt,
-               const gclm_result* res, void* cuda_stream) {
+static int solve_impl(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt, const gclm_result* res,
+                      void* cuda_stream, const gclm_packed_fields* packed) {
   if (!h || !res) return GCLM_ERR_INVALID_ARGUMENT;
-  int st = validate(prob, opt);
+  int st = validate(prob, opt, packed != nullptr);
   if (st != GCLM_OK) return st;
   if (prob->shared_intrinsics) return GCLM_ERR_INVALID_ARGUMENT;
   DeviceGuard guard(h->device);
@@ -1672,18 +1792,18 @@ int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt
   const TileCfg t = tile_config(prob->batch, prob->height, padded_width(prob->width), h->num_sms, opt->rows_per_tile,
                                 max_warps_for(prob->camera_model, use_packed()));
   const Layout L = make_layout(prob->batch, std::max(t.tiles_per_image, max_tiles_for(prob->height, prob->width)),
-                               (size_t)prob->height * padded_width(prob->width), needs_repack(prob));
+                               (size_t)prob->height * padded_width(prob->width), !packed && needs_repack(prob));
   st = ensure_scratch(h, L.total);
   if (st != GCLM_OK) return st;
-  PassArgs a = make_args(h, prob, opt, res, t, L);
+  PassArgs a = make_args(h, prob, opt, res, t, L, packed);
   const bool full = a.up && a.lat && a.uconf && a.lconf;
   lm_init_kernel<<<(prob->batch + 127) / 128, 128, 0, s>>>(a, prob->camera_init, prob->gravity_init);
   h->launches++;
-  launch_sin_plane(h, prob, a, s);
+  if (!packed) launch_sin_plane(h, prob, a, s);  // packed fields already hold sin(latitude)
   const dim3 grid((unsigned)((size_t)prob->batch * t.tiles_per_image)), block(t.nwarps * 32);
   PassTimer timer(h, s, opt->num_steps + 1);
   // small batch (the calibrate() case): every pass in ONE cooperative launch, a grid barrier between passes
-  const bool want_persistent = opt->schedule != GCLM_SCHEDULE_PER_PASS && opt->num_steps >= 1;
+  const bool want_persistent = opt->schedule != GCLM_SCHEDULE_PER_PASS && opt->num_steps >= 1 && !a.conf16;
   if (want_persistent && launch_persistent(h, a, !opt->use_log_focal, full, grid, block, s)) {
     h->launches++;
     h->persistent_solves++;
@@ -1702,6 +1822,85 @@ int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt
   }
   timer.stop();
   order.done();
+  CUDA_TRY(h, cudaGetLastError());
+  return GCLM_OK;
+}
+
+int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt,
+               const gclm_result* res, void* cuda_stream) {
+  return solve_impl(h, prob, opt, res, cuda_stream, nullptr);
+}
+
+static bool aligned_to(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) & (a - 1)) == 0; }
+
+int gclm_solve_packed(gclm_handle* h, const gclm_packed_fields* f, const gclm_problem* prob, const gclm_options* opt,
+                      const gclm_result* res, void* cuda_stream) {
+  if (!h || !f || !prob || !res) return GCLM_ERR_INVALID_ARGUMENT;
+  if (!f->up || !f->sin_lat || !f->up_conf || !f->lat_conf) return GCLM_ERR_INVALID_ARGUMENT;
+  if (f->batch != prob->batch || f->height != prob->height || f->width != prob->width) return GCLM_ERR_INVALID_ARGUMENT;
+  if (f->conf_format != GCLM_CONF_F32 && f->conf_format != GCLM_CONF_F16) return GCLM_ERR_INVALID_ARGUMENT;
+  const size_t ca = f->conf_format == GCLM_CONF_F16 ? 8 : 16;
+  if (f->width % 4 != 0 || !aligned_to(f->up, 16) || !aligned_to(f->sin_lat, 16) || !aligned_to(f->up_conf, ca) ||
+      !aligned_to(f->lat_conf, ca)) {
+    snprintf(h->last_error, sizeof(h->last_error), "packed fields: width must be a multiple of 4 and the planes aligned");
+    return GCLM_ERR_UNSUPPORTED;
+  }
+  if (f->conf_format == GCLM_CONF_F16 && !use_packed()) return GCLM_ERR_UNSUPPORTED;
+  return solve_impl(h, prob, opt, res, cuda_stream, f);
+}
+
+int gclm_pack_fields(gclm_handle* h, const gclm_problem* prob, int conf_format, float* sin_lat_out, void* up_conf_out,
+                     void* lat_conf_out, void* cuda_stream) {
+  if (!h || !prob || !sin_lat_out || !up_conf_out || !lat_conf_out) return GCLM_ERR_INVALID_ARGUMENT;
+  if (prob->batch <= 0 || prob->height <= 0 || prob->width <= 0 || !prob->latitude_field) return GCLM_ERR_INVALID_ARGUMENT;
+  if (conf_format != GCLM_CONF_F32 && conf_format != GCLM_CONF_F16) return GCLM_ERR_INVALID_ARGUMENT;
+  const size_t total = (size_t)prob->batch * prob->height * prob->width;
+  if (total % 4 != 0 || !aligned_to(prob->latitude_field, 16) || !aligned_to(sin_lat_out, 16) ||
+      (prob->up_confidence && !aligned_to(prob->up_confidence, 16)) ||
+      (prob->latitude_confidence && !aligned_to(prob->latitude_confidence, 16)) || !aligned_to(up_conf_out, 16) ||
+      !aligned_to(lat_conf_out, 16))
+    return GCLM_ERR_UNSUPPORTED;
+  DeviceGuard guard(h->device);
+  if (!guard.ok()) return GCLM_ERR_CUDA;
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  const size_t n4 = total / 4;
+  const unsigned blocks = (unsigned)std::min<size_t>((n4 + 255) / 256, (size_t)h->num_sms * 16);
+  pack_fields_kernel<<<blocks, 256, 0, s>>>(n4, reinterpret_cast<const float4*>(prob->latitude_field),
+                                            reinterpret_cast<const float4*>(prob->up_confidence),
+                                            reinterpret_cast<const float4*>(prob->latitude_confidence),
+                                            reinterpret_cast<float4*>(sin_lat_out), up_conf_out, lat_conf_out,
+                                            conf_format == GCLM_CONF_F16);
+  h->launches++;
+  CUDA_TRY(h, cudaGetLastError());
+  return GCLM_OK;
+}
+
+int gclm_pack_decoder_outputs(gclm_handle* h, int batch, int height, int width, const float* up_logits,
+                              const float* latitude_logits, const float* up_conf_logits, const float* lat_conf_logits,
+                              int conf_format, float* up_out, float* sin_lat_out, void* up_conf_out, void* lat_conf_out,
+                              void* cuda_stream) {
+  if (!h || batch <= 0 || height <= 0 || width <= 0) return GCLM_ERR_INVALID_ARGUMENT;
+  if (!up_logits || !latitude_logits || !up_conf_logits || !lat_conf_logits || !up_out || !sin_lat_out || !up_conf_out ||
+      !lat_conf_out)
+    return GCLM_ERR_INVALID_ARGUMENT;
+  if (conf_format != GCLM_CONF_F32 && conf_format != GCLM_CONF_F16) return GCLM_ERR_INVALID_ARGUMENT;
+  const size_t N = (size_t)height * width;
+  if (N % 4 != 0 || !aligned_to(up_logits, 16) || !aligned_to(latitude_logits, 16) || !aligned_to(up_conf_logits, 16) ||
+      !aligned_to(lat_conf_logits, 16) || !aligned_to(up_out, 16) || !aligned_to(sin_lat_out, 16) ||
+      !aligned_to(up_conf_out, 16) || !aligned_to(lat_conf_out, 16))
+    return GCLM_ERR_UNSUPPORTED;
+  DeviceGuard guard(h->device);
+  if (!guard.ok()) return GCLM_ERR_CUDA;
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  const size_t total4 = (size_t)batch * N / 4;
+  const unsigned blocks = (unsigned)std::min<size_t>((total4 + 255) / 256, (size_t)h->num_sms * 16);
+  pack_decoder_kernel<<<blocks, 256, 0, s>>>(batch, N / 4, reinterpret_cast<const float4*>(up_logits),
+                                             reinterpret_cast<const float4*>(latitude_logits),
+                                             reinterpret_cast<const float4*>(up_conf_logits),
+                                             reinterpret_cast<const float4*>(lat_conf_logits),
+                                             reinterpret_cast<float4*>(up_out), reinterpret_cast<float4*>(sin_lat_out),
+                                             up_conf_out, lat_conf_out, conf_format == GCLM_CONF_F16);
+  h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GCLM_OK;
 }

@@ -12,7 +12,7 @@ from typing import Dict, Optional
 import torch
 
 from . import _lib
-from ._lib import CAMERA_MODEL_IDS, Options, Problem, Result
+from ._lib import CAMERA_MODEL_IDS, Options, PackedFields, Problem, Result
 
 NUM_DIST = {"pinhole": 0, "simple_radial": 1, "radial": 2, "simple_divisional": 1}
 
@@ -102,8 +102,14 @@ class Engine:
         shared_intrinsics: bool = False,
         comm=None,
         out: Optional[Dict[str, torch.Tensor]] = None,
+        packed: Optional[Dict[str, torch.Tensor]] = None,
     ) -> Dict[str, torch.Tensor]:
-        """Enqueue one batched LM solve on the current stream; returns raw result tensors."""
+        """Enqueue one batched LM solve on the current stream; returns raw result tensors.
+
+        `packed`: pre-transformed fields from pack_fields / pack_decoder_outputs ({"up", "sin_lat", "up_conf",
+        "lat_conf"}); the four field arguments are then ignored (gclm_solve_packed)."""
+        if packed is not None:
+            up_field, latitude_field, up_confidence, latitude_confidence = packed["up"], None, None, None
         ref = up_field if up_field is not None else latitude_field
         if ref is None:
             raise _lib.GclmError("need at least one of up_field / latitude_field")
@@ -138,7 +144,22 @@ class Engine:
                         ("camera", "gravity", "covariance", "uncertainty", "costs", "stop_at", "status", "hessian_rpf")})
         stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
         # the library runs on its handle's device and restores the caller's current device (DeviceGuard)
-        if shared_intrinsics:
+        if packed is not None:
+            if shared_intrinsics:
+                raise _lib.GclmError("packed fields: per-image intrinsics only")
+            f16 = packed["up_conf"].dtype == torch.float16
+            for k in ("sin_lat", "up_conf", "lat_conf"):
+                t = packed[k]
+                if not t.is_cuda or t.device != dev or not t.is_contiguous() or t.numel() != B * H * W:
+                    raise _lib.GclmError(f"packed[{k!r}]: expected a contiguous CUDA tensor with {B * H * W} elements")
+            pf = PackedFields(batch=B, height=H, width=W, conf_format=_lib.CONF_F16 if f16 else _lib.CONF_F32,
+                              up=up_field.data_ptr(), sin_lat=packed["sin_lat"].data_ptr(),
+                              up_conf=packed["up_conf"].data_ptr(), lat_conf=packed["lat_conf"].data_ptr())
+            prob.up_field = None
+            st = self.lib.gclm_solve_packed(self._h, ctypes.byref(pf), ctypes.byref(prob), ctypes.byref(opt),
+                                            ctypes.byref(res), stream)
+            _lib.check(st, "gclm_solve_packed")
+        elif shared_intrinsics:
             comm_h = getattr(comm, "handle", comm)
             st = self.lib.gclm_solve_shared(self._h, ctypes.byref(prob), ctypes.byref(opt),
                                             ctypes.byref(res), comm_h, stream)
@@ -148,6 +169,51 @@ class Engine:
                                      ctypes.byref(res), stream)
             _lib.check(st, "gclm_solve")
         return out
+
+    # ------------------------------------------------------------------------------------------
+    def pack_fields(self, up_field: torch.Tensor, latitude_field: torch.Tensor,
+                    up_confidence: Optional[torch.Tensor], latitude_confidence: Optional[torch.Tensor], *,
+                    conf_dtype: torch.dtype = torch.float16) -> Dict[str, torch.Tensor]:
+        """gclm_pack_fields: the five activated planes -> the layout the engine streams:
+        {"up" (as given), "sin_lat" fp32, "up_conf" / "lat_conf" in `conf_dtype` (float16: 16 B/pixel/pass)}."""
+        dev = up_field.device
+        B, _, H, W = up_field.shape
+        prob = Problem(
+            batch=B, height=H, width=W, camera_model=0,
+            up_field=_dev_ptr(up_field, (B, 2, H, W), "up_field", dev),
+            latitude_field=_dev_ptr(latitude_field, (B, 1, H, W), "latitude_field", dev),
+            up_confidence=_dev_ptr(up_confidence, (B, H, W), "up_confidence", dev),
+            latitude_confidence=_dev_ptr(latitude_confidence, (B, H, W), "latitude_confidence", dev))
+        assert conf_dtype in (torch.float16, torch.float32)
+        sin_lat = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
+        uc = torch.empty((B, H, W), device=dev, dtype=conf_dtype)
+        lc = torch.empty((B, H, W), device=dev, dtype=conf_dtype)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(self.lib.gclm_pack_fields(self._h, ctypes.byref(prob),
+                                             _lib.CONF_F16 if conf_dtype == torch.float16 else _lib.CONF_F32,
+                                             sin_lat.data_ptr(), uc.data_ptr(), lc.data_ptr(), stream), "gclm_pack_fields")
+        return {"up": up_field, "sin_lat": sin_lat, "up_conf": uc, "lat_conf": lc}
+
+    def pack_decoder_outputs(self, up_logits: torch.Tensor, latitude_logits: torch.Tensor,
+                             up_conf_logits: torch.Tensor, lat_conf_logits: torch.Tensor, *,
+                             conf_dtype: torch.dtype = torch.float16) -> Dict[str, torch.Tensor]:
+        """gclm_pack_decoder_outputs: the fused decoder tail (geocalib.py:44-89) -- from the heads'
+        PRE-activation outputs straight to the streamed layout (F.normalize, clamp(tanh), sigmoid)."""
+        dev = up_logits.device
+        B, _, H, W = up_logits.shape
+        ptrs = [_dev_ptr(up_logits, (B, 2, H, W), "up_logits", dev),
+                _dev_ptr(latitude_logits, (B, 1, H, W), "latitude_logits", dev),
+                _dev_ptr(up_conf_logits, (B, H, W), "up_conf_logits", dev),
+                _dev_ptr(lat_conf_logits, (B, H, W), "lat_conf_logits", dev)]
+        up = torch.empty((B, 2, H, W), device=dev, dtype=torch.float32)
+        sin_lat = torch.empty((B, 1, H, W), device=dev, dtype=torch.float32)
+        uc = torch.empty((B, H, W), device=dev, dtype=conf_dtype)
+        lc = torch.empty((B, H, W), device=dev, dtype=conf_dtype)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(self.lib.gclm_pack_decoder_outputs(
+            self._h, B, H, W, *ptrs, _lib.CONF_F16 if conf_dtype == torch.float16 else _lib.CONF_F32,
+            up.data_ptr(), sin_lat.data_ptr(), uc.data_ptr(), lc.data_ptr(), stream), "gclm_pack_decoder_outputs")
+        return {"up": up, "sin_lat": sin_lat, "up_conf": uc, "lat_conf": lc}
 
     # ------------------------------------------------------------------------------------------
     def system(self, camera_model: str, up_field, latitude_field, up_confidence, latitude_confidence,

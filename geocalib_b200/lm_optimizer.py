@@ -49,7 +49,12 @@ def get_trivial_estimation(data: Dict[str, torch.Tensor], camera_model) -> Tuple
 
     Returns raw tensors (camera (B,8) float32, gravity (B,3) float32) on the fields' device.
     """
-    ref = data["up_field"] if "up_field" in data else data["latitude_field"]
+    if "up_field" in data:
+        ref = data["up_field"]
+    elif "latitude_field" in data:
+        ref = data["latitude_field"]
+    else:
+        ref = data["packed_fields"]["up"]  # pre-transformed fields (Engine.pack_*): shape and device only
     ref = ref.detach()
     B = ref.shape[0]
     h, w = ref.shape[-2:]
@@ -107,6 +112,9 @@ class LMOptimizer(nn.Module):
         "stop_mode": "batch",  # "batch" (reference semantics) | "per_image"
         "rows_per_tile": 0,
         "schedule": "auto",  # "auto" | "per_pass" | "persistent" (one cooperative launch; small batches)
+        # "float16": the fields are transformed once per solve into the 16 B/pixel layout (sin(latitude) + fp16
+        # confidences, gclm_pack_fields) and every pass streams that instead of 20 B/pixel
+        "confidence_dtype": "float32",
     }
 
     def __init__(self, conf: Optional[Dict[str, Any]] = None):
@@ -189,11 +197,13 @@ class LMOptimizer(nn.Module):
         """
         cam0 = camera_init._data if hasattr(camera_init, "_data") else camera_init
         g0 = gravity_init._data if hasattr(gravity_init, "_data") else gravity_init
+        packed = data.get("packed_fields")  # pre-transformed by the caller (Engine.pack_decoder_outputs / pack_fields)
         up = self._field(data, "up_field", 2)
         lat = self._field(data, "latitude_field", 1)
-        ref = up if up is not None else lat
+        ref = packed["up"] if packed is not None else (up if up is not None else lat)
         if ref is None:
             raise KeyError("latitude_field")
+        has_up, has_lat = packed is not None or up is not None, packed is not None or lat is not None
         if not ref.is_cuda:
             raise _lib.GclmError(
                 "geocalib_b200.LMOptimizer runs on CUDA tensors only (fields are on "
@@ -211,27 +221,30 @@ class LMOptimizer(nn.Module):
                 "backward pass; call it under torch.no_grad() or detach the fields")
         name = self.camera_model.name()
         eng = get_engine(ref.device)
+        if packed is None and self.conf.confidence_dtype == "float16" and up is not None and lat is not None \
+                and not self.shared_intrinsics and ref.shape[-1] % 4 == 0:
+            packed = eng.pack_fields(up, lat, uconf, lconf, conf_dtype=torch.float16)
         raw = eng.solve(
             name, up, lat, uconf, lconf,
             cam0.detach().float().contiguous().to(ref.device), g0.detach().float().contiguous().to(ref.device),
             options=self._options(), estimate_gravity=self.estimate_gravity,
             estimate_focal=self.estimate_focal, estimate_dist=self.estimate_dist,
-            shared_intrinsics=bool(self.shared_intrinsics), comm=self.comm,
+            shared_intrinsics=bool(self.shared_intrinsics), comm=self.comm, packed=packed,
         )
         costs = raw["costs"]
         infos: Dict[str, torch.Tensor] = {"stop_at": raw["stop_at"].to(torch.float32)}
-        if up is not None:
+        if has_up:
             infos["initial_up_cost"] = costs[:, 1]
-        if lat is not None:
+        if has_lat:
             infos["initial_latitude_cost"] = costs[:, 2]
         infos["initial_cost"] = costs[:, 0]
         if not self.training:
             infos["covariance"] = raw["covariance"]
             for i, k in enumerate(UNCERTAINTY_KEYS):
                 infos[k] = raw["uncertainty"][:, i]
-        if up is not None:
+        if has_up:
             infos["final_up_cost"] = costs[:, 4]
-        if lat is not None:
+        if has_lat:
             infos["final_latitude_cost"] = costs[:, 5]
         infos["final_cost"] = costs[:, 3]
         infos["status"] = raw["status"]

@@ -168,6 +168,37 @@ int gclm_solve(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt
                const gclm_result* res, void* cuda_stream);
 
 /*
+ * Pre-transformed field layout.  The CNN heads end in F.normalize / asin(clamp(tanh)) /
+ * sigmoid and write five fp32 planes (geocalib.py:44-89); the LM immediately takes sin() of the latitude
+ * (lm_optimizer.py:270) -- the asin cancels.  This layout is what the engine actually streams:
+ *   up (B,2,H,W) unit vectors, sin_lat (B,1,H,W) = sin(latitude), up_conf / lat_conf (B,H,W) in fp32
+ *   (20 B/pixel/pass) or fp16 (16 B/pixel/pass).
+ * gclm_pack_decoder_outputs builds it from the heads' PRE-activation outputs (the fused decoder tail: one
+ * write instead of five planes + a sin pass); gclm_pack_fields builds it from the five activated planes
+ * (up is used in place).  All buffers are caller-owned device memory; width % 4 == 0 and 16-byte aligned
+ * planes are required (GCLM_ERR_UNSUPPORTED otherwise).  gclm_solve_packed is gclm_solve on such fields:
+ * `prob` supplies everything except the field pointers (ignored).  fp16 confidences perturb the weights
+ * by <= 2^-11 relative, zero-mean: measured parity in tests/test_gpu_packed.py.
+ */
+typedef enum { GCLM_CONF_F32 = 0, GCLM_CONF_F16 = 1 } gclm_conf_format;
+typedef struct {
+  int32_t batch, height, width;
+  int32_t conf_format;  /* gclm_conf_format */
+  const float* up;      /* (B,2,H,W) */
+  const float* sin_lat; /* (B,1,H,W) */
+  const void* up_conf;  /* (B,H,W) float or half */
+  const void* lat_conf; /* (B,H,W) float or half */
+} gclm_packed_fields;
+int gclm_pack_fields(gclm_handle* h, const gclm_problem* prob, int conf_format, float* sin_lat_out,
+                     void* up_conf_out, void* lat_conf_out, void* cuda_stream);
+int gclm_pack_decoder_outputs(gclm_handle* h, int batch, int height, int width, const float* up_logits,
+                              const float* latitude_logits, const float* up_conf_logits,
+                              const float* lat_conf_logits, int conf_format, float* up_out, float* sin_lat_out,
+                              void* up_conf_out, void* lat_conf_out, void* cuda_stream);
+int gclm_solve_packed(gclm_handle* h, const gclm_packed_fields* fields, const gclm_problem* prob,
+                      const gclm_options* opt, const gclm_result* res, void* cuda_stream);
+
+/*
  * Diagnostic: the reduced Gauss-Newton system of ONE pass at the given parameters, i.e. what
  * LMOptimizer.setup_system + calculate_costs return (lm_optimizer.py:276-315, 387-461), with the full
  * column set [g0 g1 | f | k..] (NF = 3 + num_dist): gradient (B,NF) = J^T W r, hessian (B,NF,NF) =
