@@ -325,11 +325,12 @@ class ReferenceRunner:
         return self.per_worker * self.procs
 
     def size_step(self, seconds):
-        """Pick per_worker in [1, chunk] so that a step takes about `seconds`."""
-        self.per_worker = 1
-        dt1 = self.step()
-        self.per_worker = int(max(1, min(self.chunk, seconds // max(dt1, 1e-3))))
-        return dt1
+        """Pick per_worker in [1, chunk] so that a step takes about `seconds` (timed at the full chunk: the
+        reference is super-linear in the images per call, one image says nothing about eight)."""
+        self.per_worker = self.chunk
+        dt = self.step()
+        self.per_worker = int(max(1, min(self.chunk, self.chunk * seconds / max(dt, 1e-3))))
+        return dt
 
     def describe(self):
         return (f"{self.images_per_step} images of the workload ({self.h}x{self.w} {self.model}, {self.iters} LM "

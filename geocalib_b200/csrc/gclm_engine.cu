@@ -53,12 +53,17 @@ constexpr int SCHUR_NSUM = 25;
 // Which pass a CTA is working on: a kernel parameter for the one-launch-per-pass schedule, a loop variable in
 // the persistent small-batch kernel.
 struct PassId { int pass, is_final; };
+#ifdef GCLM_PHASE_TIMERS
+#define GCLM_STAMP(k) do { if (threadIdx.x == 0 && a.dbg) a.dbg[((size_t)pid.pass * gridDim.x + blockIdx.x) * 8 + (k)] = clock64(); } while (0)
+#else
+#define GCLM_STAMP(k) do {} while (0)
+#endif
 
 struct Ctrl {
   int stop;            // batch-global early stop fired: later LM passes are no-ops
   int stop_at;         // first iteration (1-based) at which all images were converged
-  unsigned done[2];    // images finished in the current pass (ping-pong by pass parity)
-  unsigned unconv[2];  // images NOT converged in the current pass
+  unsigned long long vote[2];  // batch stop vote of the current pass (ping-pong by pass parity):
+                               // low word = images that voted, high word = images NOT converged
   unsigned img_done;   // shared intrinsics: images whose Schur partials of this pass are written
   int comm_error;      // sticky: a peer's contribution never arrived (fused exchange timed out)
   unsigned bar;        // persistent kernel: grid barrier arrivals (monotone within a solve)
@@ -109,6 +114,7 @@ struct PassArgs {
   // (pp) and applies the update; 0 = separate kernels around an NCCL all-reduce (fallback)
   int fused_shared;
   float* shared_sums;  // (SCHUR_NSUM + 1) all-reduced sums of the current step
+  long long* dbg;      // GCLM_PHASE_TIMERS build: clock64 stamps [pass][cta][8]
   P2PArgs pp;
   int final_rpf;       // basis of the final pass: 1 = (roll,pitch) + linear focal (covariance), 0 = LM basis
   float *sys_g, *sys_h, *sys_cost;
@@ -193,17 +199,26 @@ __device__ __forceinline__ int active_columns(int model, int est_gravity, int es
   return n;
 }
 
+// What thread 0 of every CTA reads about its image in the prologue (one round trip to L2, all loads
+// independent) and the solver of the image's last CTA re-uses from shared memory instead of reading again.
+struct ImgState {
+  float P[PSTRIDE];  // current parameters: cam[8], g[3]
+  float lam, prev_cost;
+  int slot;
+  unsigned flags;
+};
+
 // ---------------------------------------------------------------------------------------------
 // per-image epilogue, executed by ONE thread of the last CTA of the image
 // ---------------------------------------------------------------------------------------------
 template <int MODEL>
-__device__ __noinline__ void finalize_image(const PassArgs& a, int b, const float* sums, int sl) {
+__device__ __noinline__ void finalize_image(const PassArgs& a, int b, const float* sums, const ImgState& st) {
   constexpr int K = Dims<MODEL>::K, NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH;
   const float invN = 1.f / ((float)a.H * (float)a.Wt);
   const float cu = sums[NH + NF] * (a.up_scale * a.up_scale) * invN;
   const float cl = sums[NH + NF + 1] * (a.lat_scale * a.lat_scale) * invN;
-  const float* Pb = a.P + ((size_t)b * 2 + sl) * PSTRIDE;
-  unsigned fl = a.flags[b] & 0xffu;
+  const float* Pb = st.P;
+  unsigned fl = __ldcg(&a.flags[b]) & 0xffu;
   int act[NF];
   const int n = active_columns(MODEL, a.est_gravity, a.est_focal, act);
   float Hf[NF][NF];
@@ -269,26 +284,24 @@ __device__ __forceinline__ bool allclose1(float nw, float prev, float atol, floa
 __device__ __forceinline__ void batch_stop_vote(const PassArgs& a, const PassId pid, bool converged) {
   Ctrl* c = a.ctrl;
   const int par = pid.pass & 1;
-  if (!converged) atomicAdd(&c->unconv[par], 1u);
-  __threadfence();
-  const unsigned t = atomicAdd(&c->done[par], 1u);
-  if (t == (unsigned)a.B - 1u) {
-    __threadfence();
-    const unsigned un = atomicAdd(&c->unconv[par], 0u);
-    if (un == 0u) {
+  // ONE atomic carries both counts; its return value tells the last voter everything (no fences, no second
+  // round trip: what the vote decides is read after the next kernel boundary / grid barrier only)
+  const unsigned long long mine = 1ull + (converged ? 0ull : (1ull << 32));
+  const unsigned long long before = atomicAdd(&c->vote[par], mine);
+  if ((unsigned)(before & 0xffffffffull) == (unsigned)a.B - 1u) {
+    const unsigned long long un = (before + mine) >> 32;
+    if (un == 0ull) {
       if (pid.pass < c->stop_at) c->stop_at = pid.pass;  // infos["stop_at"] = min(i + 1, ...)
       if (a.early_stop) c->stop = 1;
     }
-    c->done[par ^ 1] = 0u;  // arm the counters of the next pass
-    c->unconv[par ^ 1] = 0u;
-    __threadfence();
+    c->vote[par ^ 1] = 0ull;  // arm the counter of the next pass
   }
 }
 
 template <int MODEL>
-__device__ __noinline__ void lm_step_image(const PassArgs& a, const PassId pid, int b, const float* sums) {
+__device__ __noinline__ void lm_step_image(const PassArgs& a, const PassId pid, int b, const float* sums, const ImgState& st) {
   constexpr int K = Dims<MODEL>::K, NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH;
-  int sl = a.slot[b];
+  const int sl = st.slot;
   if (pid.is_final) {
     if (a.sys_h) {  // gclm_system: hand the reduced system out as it is (full columns [g0 g1 f k..])
       const float invN = 1.f / ((float)a.H * (float)a.Wt);
@@ -306,21 +319,20 @@ __device__ __noinline__ void lm_step_image(const PassArgs& a, const PassId pid, 
       }
       return;
     }
-    if (a.ctrl->stop) sl ^= 1;  // batch stop fired: the tentative update of that pass is dropped
-    finalize_image<MODEL>(a, b, sums, sl);
+    finalize_image<MODEL>(a, b, sums, st);  // st.P: the final estimate (the prologue applied the stop rule)
     return;
   }
   const float invN = 1.f / ((float)a.H * (float)a.Wt);
   const float cu = sums[NH + NF] * (a.up_scale * a.up_scale) * invN;
   const float cl = sums[NH + NF + 1] * (a.lat_scale * a.lat_scale) * invN;
   const float cost = cu + cl;  // lm_optimizer.py:584,610
-  float lam = a.lam[b];
+  float lam = st.lam;
   bool converged = false;
   if (pid.pass == 0) {
     a.cost0[b * 3] = cost; a.cost0[b * 3 + 1] = cu; a.cost0[b * 3 + 2] = cl;
   } else {
     // this pass evaluated cost(theta_i) == "new_cost" of iteration i-1 (lm_optimizer.py:607-613)
-    const float prev = a.prev_cost[b];
+    const float prev = st.prev_cost;
     if (!a.fix_lambda) lam = fminf(fmaxf(lam * (cost > prev ? 10.f : 0.1f), 1e-6f), 1e2f);
     converged = allclose1(cost, prev, a.atol, a.rtol);
     if (a.stop_mode == GCLM_STOP_PER_IMAGE && converged) {
@@ -374,7 +386,7 @@ __device__ __noinline__ void lm_step_image(const PassArgs& a, const PassId pid, 
     a.flags[b] |= GCLM_STATUS_CHOLESKY_FAILED;
   }
   // ---- update_estimate (lm_optimizer.py:518-549) into the other parameter buffer ----
-  const float* Pc = a.P + ((size_t)b * 2 + sl) * PSTRIDE;
+  const float* Pc = st.P;
   float* Pn = a.P + ((size_t)b * 2 + (sl ^ 1)) * PSTRIDE;
   float cam[8], g[3];
   for (int i = 0; i < 8; i++) cam[i] = Pc[i];
@@ -404,7 +416,7 @@ __device__ __noinline__ void lm_step_image(const PassArgs& a, const PassId pid, 
 // <= 25 sums cross images (and GPUs): one tiny all-reduce per LM step.
 // ---------------------------------------------------------------------------------------------
 template <int MODEL>
-__device__ __noinline__ void schur_image(const PassArgs& a, const PassId pid, int b, const float* sums) {
+__device__ __noinline__ void schur_image(const PassArgs& a, const PassId pid, int b, const float* sums, const ImgState& st) {
   constexpr int NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH;
   const float invN = 1.f / ((float)a.H * (float)a.Wt);
   const float cu = sums[NH + NF] * (a.up_scale * a.up_scale) * invN;
@@ -412,7 +424,7 @@ __device__ __noinline__ void schur_image(const PassArgs& a, const PassId pid, in
   const float cost = cu + cl;
   bool converged = false;
   if (pid.pass == 0) { a.cost0[b * 3] = cost; a.cost0[b * 3 + 1] = cu; a.cost0[b * 3 + 2] = cl; }
-  else converged = allclose1(cost, a.prev_cost[b], a.atol, a.rtol);
+  else converged = allclose1(cost, st.prev_cost, a.atol, a.rtol);
   a.prev_cost[b] = cost;
   int act[NF];
   const int n = active_columns(MODEL, a.est_gravity, a.est_focal, act);
@@ -680,26 +692,45 @@ __device__ __forceinline__ void
   using V = typename std::conditional<PACK, f2, float>::type;  // 2 pixels per op when packed
   const int b = blockIdx.x / a.tiles_per_image;
   const int tile = blockIdx.x - b * a.tiles_per_image;
-  if (!pid.is_final) {
-    if (*(volatile int*)&a.ctrl->stop) return;
-    if (a.flags[b] & FLAG_FROZEN) return;
-  }
+  GCLM_STAMP(0);
   __shared__ PassConst s_pc;
   __shared__ RobustConst s_rc;
+  __shared__ ImgState s_img;
   __shared__ float s_red[MAX_WARPS][NACC];
   __shared__ float s_sum[NACC];
   __shared__ int s_last;
   __shared__ int s_last_img;
+  __shared__ int s_skip;
   __shared__ float s_part[MAX_WARPS][SCHUR_NSUM + 3];
   __shared__ float s_tot[SCHUR_NSUM + 3];
   if (threadIdx.x == 0) {
-    int sl = a.slot[b];
-    if (pid.is_final && a.ctrl->stop) sl ^= 1;
-    const float* Pb = a.P + ((size_t)b * 2 + sl) * PSTRIDE;
-    make_pass_const(Pb, Pb + 8, a.spherical != 0, a.log_focal != 0, pid.is_final != 0 && a.final_rpf != 0, s_pc);
-    s_rc = make_robust_const(a.up_scale, a.lat_scale);
+    // everything this CTA (and, if it turns out to be the image's last one, its solver) needs to know about the
+    // image: independent L2 loads, ONE round trip (both parameter buffers are fetched, the slot picks one)
+    const int stop = __ldcg(&a.ctrl->stop);
+    const int sl0 = __ldcg(&a.slot[b]);
+    const unsigned fl = __ldcg(&a.flags[b]);
+    const float lam = __ldcg(&a.lam[b]), prev = __ldcg(&a.prev_cost[b]);
+    const float4* P4 = reinterpret_cast<const float4*>(a.P + (size_t)b * 2 * PSTRIDE);
+    float4 q[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) q[i] = __ldcg(P4 + i);
+    int sl = sl0;
+    if (pid.is_final && stop) sl ^= 1;  // batch stop fired: the tentative update of that pass is dropped
+    const float4 p0 = sl ? q[3] : q[0], p1 = sl ? q[4] : q[1], p2 = sl ? q[5] : q[2];
+    s_img.P[0] = p0.x; s_img.P[1] = p0.y; s_img.P[2] = p0.z; s_img.P[3] = p0.w;
+    s_img.P[4] = p1.x; s_img.P[5] = p1.y; s_img.P[6] = p1.z; s_img.P[7] = p1.w;
+    s_img.P[8] = p2.x; s_img.P[9] = p2.y; s_img.P[10] = p2.z; s_img.P[11] = p2.w;
+    s_img.lam = lam; s_img.prev_cost = prev; s_img.slot = sl0; s_img.flags = fl;
+    const int skip = !pid.is_final && (stop || (fl & FLAG_FROZEN));
+    s_skip = skip;
+    if (!skip) {
+      make_pass_const(s_img.P, s_img.P + 8, a.spherical != 0, a.log_focal != 0, pid.is_final != 0 && a.final_rpf != 0, s_pc);
+      s_rc = make_robust_const(a.up_scale, a.lat_scale);
+    }
   }
   __syncthreads();
+  if (s_skip) return;  // batch stop latched / image frozen: this pass is a no-op for the CTA
+  GCLM_STAMP(1);
   const PassConst pc = s_pc;
   const FieldMask fm = {a.up != nullptr, a.lat != nullptr, a.uconf != nullptr, a.lconf != nullptr};
   const RobustConst rc = s_rc;
@@ -747,7 +778,54 @@ __device__ __forceinline__ void
     __syncwarp();
   }
 #endif
-  for (int job = warp; job < NS * a.rsub; job += nwarps) {
+  bool small_done = false;
+#if !defined(GCLM_TMA) && !defined(GCLM_TMA2D)
+  if constexpr (IN == 1 && RING_STAGES > 0) {
+    if (RJ == 1) {
+      // Tiny tiles (small batches: the calibrate() case): every job is ONE row of one strip, so the row ring has
+      // nothing to prefetch within a job.  Instead the rows of up to RING_STAGES jobs of this warp are fetched
+      // together (one L2 / HBM round trip instead of one per job) and then computed.  Same pixels, same
+      // per-lane accumulation order as the generic loop below (jobs in increasing order) -> same sums.
+      const unsigned plane_stride = blockDim.x * 16u, stage_stride = 5u * plane_stride;
+      const unsigned slot0 = smem_u32 + threadIdx.x * 16u;
+      const int njobs = NS * a.rsub;
+      for (int j0 = warp; j0 < njobs; j0 += nwarps * RING_STAGES) {
+#pragma unroll
+        for (int st = 0; st < RING_STAGES; st++) {
+          const int job = j0 + st * nwarps;
+          const int strip = job % NS, y = yt0 + job / NS, x0 = (strip << 7) + (lane << 2);
+          if (job < njobs && x0 < W && y < yt1) {
+            const size_t off = (size_t)y * W + x0;
+            const unsigned d = slot0 + st * stage_stride;
+            cp_async16(d, a.up + (size_t)b * 2 * N + off); cp_async16(d + plane_stride, a.up + (size_t)b * 2 * N + N + off);
+            cp_async16(d + 2u * plane_stride, a.lat + (size_t)b * N + off);
+            cp_async16(d + 3u * plane_stride, a.uconf + (size_t)b * N + off);
+            cp_async16(d + 4u * plane_stride, a.lconf + (size_t)b * N + off);
+          }
+        }
+        cp_async_commit();
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int st = 0; st < RING_STAGES; st++) {
+          const int job = j0 + st * nwarps;
+          const int strip = job % NS, y = yt0 + job / NS, x0 = (strip << 7) + (lane << 2);
+          if (job < njobs && x0 < W && y < yt1) {
+            float u[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) u[i] = pixel_u(pc, x0 + i);
+            const unsigned d = slot0 + st * stage_stride;
+            const float4 ox = lds128(d), oy = lds128(d + plane_stride), ol = lds128(d + 2u * plane_stride);
+            const float4 cu = lds128(d + 3u * plane_stride), cl = lds128(d + 4u * plane_stride);
+            row_accumulate<MODEL, GEN_D, FULL, PACK>(pc, fm, make_row_cols<PACK>(pc, u), pixel_v(pc, y), ox, oy, ol, cu, cl,
+                                                     rc, acc, &s_pc, &s_rc);
+          }
+        }
+      }
+      small_done = true;
+    }
+  }
+#endif
+  for (int job = warp; !small_done && job < NS * a.rsub; job += nwarps) {
     const int strip = job % NS, sub = job / NS;
     const int x0 = (strip << 7) + (lane << 2);
     const int y0 = yt0 + sub * RJ, y1 = min(yt1, y0 + RJ);
@@ -932,6 +1010,7 @@ __device__ __forceinline__ void
   }
 
   // ---- CTA reduction: shuffle tree, then fixed-order sum over warps ----
+  GCLM_STAMP(2);
 #pragma unroll
   for (int i = 0; i < NACC; i++) {
     float x = hsum(acc[i]);
@@ -951,6 +1030,7 @@ __device__ __forceinline__ void
     else { a.partials[((size_t)b * S + tile) * NACC + threadIdx.x] = s; __threadfence(); }
   }
   __syncthreads();
+  GCLM_STAMP(3);
   if (S > 1) {
     if (threadIdx.x == 0) {
       const unsigned t = atomicAdd(&a.tickets[b], 1u);
@@ -958,29 +1038,40 @@ __device__ __forceinline__ void
     }
     __syncthreads();
     if (!s_last) return;
+    GCLM_STAMP(4);
     __threadfence();
     if (threadIdx.x < NACC) {  // deterministic: tile order, independent of arrival order
       float s = 0.f;
       const float* p = a.partials + (size_t)b * S * NACC + threadIdx.x;
-      for (int t = 0; t < S; t++) s += __ldcg(p + (size_t)t * NACC);
+      int t = 0;
+      for (; t + 8 <= S; t += 8) {  // 8 independent loads in flight, added in tile order
+        float x[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) x[k] = __ldcg(p + (size_t)(t + k) * NACC);
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += x[k];
+      }
+      for (; t < S; t++) s += __ldcg(p + (size_t)t * NACC);
       s_sum[threadIdx.x] = s;
     }
     __syncthreads();
   }
+  GCLM_STAMP(5);
   if (threadIdx.x == 0) {
     a.tickets[b] = 0u;
     finish_sums<MODEL, GEN_D>(s_sum, pc.k1, pc.k2, a.up_scale);  // [g0 g1 X k..] x 1/a_up -> [g0 g1 f k..]
     s_last_img = 0;
     if (a.shared && !pid.is_final) {
-      schur_image<MODEL>(a, pid, b, s_sum);
+      schur_image<MODEL>(a, pid, b, s_sum, s_img);
       if (a.fused_shared) {  // image-level ticket: the last image's CTA finishes the LM step for the batch
         __threadfence();
         if (atomicAdd(&a.ctrl->img_done, 1u) == (unsigned)a.B - 1u) { a.ctrl->img_done = 0u; s_last_img = 1; }
       }
     } else {
-      lm_step_image<MODEL>(a, pid, b, s_sum);
+      lm_step_image<MODEL>(a, pid, b, s_sum, s_img);
     }
   }
+  GCLM_STAMP(6);
   if (a.shared && a.fused_shared && !pid.is_final) {  // uniform over the grid
     __syncthreads();
     if (s_last_img) shared_tail<MODEL>(a, pid, s_part, s_tot);
@@ -1029,6 +1120,9 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
     pass_body<MODEL, GEN_D, FULL ? 1 : 0, PACK>(a, PassId{p, 0});
     target += gridDim.x;
     grid_barrier(a.ctrl, target);
+#ifdef GCLM_PHASE_TIMERS
+    if (threadIdx.x == 0 && a.dbg) a.dbg[((size_t)p * gridDim.x + blockIdx.x) * 8 + 7] = clock64();
+#endif
   }
   pass_body<MODEL, true, FULL ? 1 : 0, PACK>(a, PassId{a.num_steps, 1});
 }
@@ -1041,8 +1135,7 @@ __global__ void lm_init_kernel(PassArgs a, const float* cam0, const float* g0) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b == 0) {
     a.ctrl->stop = 0; a.ctrl->stop_at = a.num_steps;
-    a.ctrl->done[0] = a.ctrl->done[1] = 0u;
-    a.ctrl->unconv[0] = a.ctrl->unconv[1] = 0u;
+    a.ctrl->vote[0] = a.ctrl->vote[1] = 0ull;
     a.ctrl->img_done = 0u; a.ctrl->comm_error = 0; a.ctrl->bar = 0u;
   }
   if (b >= a.B) return;
@@ -1253,6 +1346,7 @@ struct gclm_handle {
   int tpasses[TIMED] = {};
   int64_t tcount = 0;
   char last_error[256] = {0};
+  long long* dbg = nullptr;  // GCLM_PHASE_TIMERS build only
 };
 
 // Event pair around the pass launches of one solve (only when timing is on; never while capturing).
@@ -1388,7 +1482,12 @@ TileCfg tile_config(int B, int H, int W, int num_sms, int rows_override, int max
   int rj = std::max(1, ((H + tiles - 1) / tiles + t.rsub - 1) / t.rsub);
   if (rows_override > 0) rj = std::max(1, rows_override / t.rsub);
   else
+  {
     while (rj >= 8 && (int64_t)B * ((H + rj * t.rsub - 1) / (rj * t.rsub)) < 12ll * num_sms) rj /= 2;  // stays >= 4
+    // tiny batches (a handful of images: the calibrate() case) are latency-bound: as many CTAs as the image
+    // allows, down to single-row jobs (rows_per_tile stays >= 4, which is what gclm_reserve sizes for)
+    while (rj >= 2 && (rj / 2) * t.rsub >= 4 && (int64_t)B * ((H + rj * t.rsub - 1) / (rj * t.rsub)) < num_sms / 2) rj /= 2;
+  }
   t.rows_per_tile = rj * t.rsub;
   t.tiles_per_image = (H + t.rows_per_tile - 1) / t.rows_per_tile;
   return t;
@@ -1642,6 +1741,11 @@ PassArgs make_args(gclm_handle* h, const gclm_problem* p, const gclm_options* o,
   a.schur = reinterpret_cast<float*>(base + L.schur);
   a.res = *r;
   a.final_rpf = 1;
+#ifdef GCLM_PHASE_TIMERS
+  if (!h->dbg) { cudaMalloc(reinterpret_cast<void**>(&h->dbg), sizeof(long long) * 8 * 64 * 1024); }
+  cudaMemsetAsync(h->dbg, 0, sizeof(long long) * 8 * 64 * 1024);
+  a.dbg = h->dbg;
+#endif
   return a;
 }
 
@@ -1745,6 +1849,13 @@ int gclm_reserve(gclm_handle* h, int batch, int height, int width) {
 
 int64_t gclm_launch_count(const gclm_handle* h) { return h ? h->launches : 0; }
 int64_t gclm_persistent_count(const gclm_handle* h) { return h ? h->persistent_solves : 0; }
+#ifdef GCLM_PHASE_TIMERS
+int gclm_debug_stamps(gclm_handle* h, long long* out, int n) {  // debug build: copy the first n stamps to the host
+  if (!h || !h->dbg) return -1;
+  cudaDeviceSynchronize();
+  return cudaMemcpy(out, h->dbg, sizeof(long long) * n, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+#endif
 
 int gclm_tile_config(int batch, int height, int width, int camera_model, int num_sms, int rows_per_tile,
                      int32_t out[5]) {
