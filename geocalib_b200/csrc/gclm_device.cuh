@@ -782,20 +782,27 @@ GCLM_HD inline void cholesky_solve(const float* L, int n, float* b) {
 // (the runtime-n versions above index local-memory arrays).  Same operations in the same order -> same bits.
 template <int N>
 GCLM_HD __forceinline__ bool cholesky_solve_fixed(float (&A)[N][N], float (&b)[N]) {
+  // One reciprocal square root per column instead of a square root and N divisions (IEEE sqrt and division are
+  // ~100-cycle dependent instruction sequences; this runs on ONE thread per image and is on the critical path of
+  // small batches).  id[j] = 1 / L[j][j].
+  float id[N];
 #pragma unroll
   for (int j = 0; j < N; j++) {
     float d = A[j][j];
 #pragma unroll
     for (int k = 0; k < j; k++) d -= A[j][k] * A[j][k];
     if (!(d > 0.f)) return false;
-    d = sqrtf(d);
-    A[j][j] = d;
+#ifdef __CUDA_ARCH__
+    id[j] = __frsqrt_rn(d);
+#else
+    id[j] = 1.f / sqrtf(d);
+#endif
 #pragma unroll
     for (int i = j + 1; i < N; i++) {
       float t = A[i][j];
 #pragma unroll
       for (int k = 0; k < j; k++) t -= A[i][k] * A[j][k];
-      A[i][j] = t / d;
+      A[i][j] = t * id[j];
     }
   }
 #pragma unroll
@@ -803,14 +810,58 @@ GCLM_HD __forceinline__ bool cholesky_solve_fixed(float (&A)[N][N], float (&b)[N
     float t = b[i];
 #pragma unroll
     for (int k = 0; k < i; k++) t -= A[i][k] * b[k];
-    b[i] = t / A[i][i];
+    b[i] = t * id[i];
   }
 #pragma unroll
   for (int i = N - 1; i >= 0; i--) {
     float t = b[i];
 #pragma unroll
     for (int k = i + 1; k < N; k++) t -= A[k][i] * b[k];
-    b[i] = t / A[i][i];
+    b[i] = t * id[i];
+  }
+  return true;
+}
+
+// Inverse of a symmetric positive definite matrix through its Cholesky factor, compile-time size, registers
+// only.  Returns false when A is not positive definite (the caller then takes the pivoting inverse below).
+template <int N>
+GCLM_HD __forceinline__ bool spd_inverse_fixed(const float (&A)[N][N], float (&Ainv)[N][N]) {
+  float L[N][N];
+#pragma unroll
+  for (int j = 0; j < N; j++) {
+    float d = A[j][j];
+#pragma unroll
+    for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k];
+    if (!(d > 0.f)) return false;
+    d = sqrtf(d);
+    L[j][j] = d;
+#pragma unroll
+    for (int i = j + 1; i < N; i++) {
+      float t = A[i][j];
+#pragma unroll
+      for (int k = 0; k < j; k++) t -= L[i][k] * L[j][k];
+      L[i][j] = t / d;
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < N; c++) {  // solve L L^T x = e_c
+    float y[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      float t = i == c ? 1.f : 0.f;
+#pragma unroll
+      for (int k = 0; k < i; k++) t -= L[i][k] * y[k];
+      y[i] = t / L[i][i];
+    }
+#pragma unroll
+    for (int i = N - 1; i >= 0; i--) {
+      float t = y[i];
+#pragma unroll
+      for (int k = i + 1; k < N; k++) t -= L[k][i] * y[k];
+      y[i] = t / L[i][i];
+    }
+#pragma unroll
+    for (int i = 0; i < N; i++) Ainv[i][c] = y[i];
   }
   return true;
 }

@@ -55,8 +55,10 @@ constexpr int SCHUR_NSUM = 25;
 struct PassId { int pass, is_final; };
 #ifdef GCLM_PHASE_TIMERS
 #define GCLM_STAMP(k) do { if (threadIdx.x == 0 && a.dbg) a.dbg[((size_t)pid.pass * gridDim.x + blockIdx.x) * 8 + (k)] = clock64(); } while (0)
+#define GCLM_SOLVER_STAMP(k) do { if (a.dbg) a.dbg[400000 + pid.pass * 8 + (k)] = clock64(); } while (0)
 #else
 #define GCLM_STAMP(k) do {} while (0)
+#define GCLM_SOLVER_STAMP(k) do {} while (0)
 #endif
 
 struct Ctrl {
@@ -66,7 +68,8 @@ struct Ctrl {
                                // low word = images that voted, high word = images NOT converged
   unsigned img_done;   // shared intrinsics: images whose Schur partials of this pass are written
   int comm_error;      // sticky: a peer's contribution never arrived (fused exchange timed out)
-  unsigned bar;        // persistent kernel: grid barrier arrivals (monotone within a solve)
+  unsigned bar_count;  // persistent kernel: arrivals at the current grid barrier (0 between barriers)
+  unsigned bar_gen;    // ... and its generation (sense reversal: safe across solves and CUDA-graph replays)
 };
 
 // One-shot all-reduce over NVLink peer memory, fused into the pass kernel's epilogue: every rank stores its
@@ -115,6 +118,10 @@ struct PassArgs {
   int fused_shared;
   float* shared_sums;  // (SCHUR_NSUM + 1) all-reduced sums of the current step
   long long* dbg;      // GCLM_PHASE_TIMERS build: clock64 stamps [pass][cta][8]
+  // persistent schedule with the set-up folded in (no lm_init_kernel / sin_plane_kernel launches)
+  int fused_init;
+  const float *cam0, *g0;   // (B,8), (B,3) initial estimate (gclm_problem.camera_init / gravity_init)
+  const float* lat_raw;     // (B,1,H,W) latitude in radians; a.lat is the sin() plane in scratch
   P2PArgs pp;
   int final_rpf;       // basis of the final pass: 1 = (roll,pitch) + linear focal (covariance), 0 = LM basis
   float *sys_g, *sys_h, *sys_cost;
@@ -235,7 +242,22 @@ __device__ __noinline__ void finalize_image(const PassArgs& a, int b, const floa
   if (a.compute_unc && (a.res.covariance || a.res.uncertainty)) {
     float Cv[MAX_NF * MAX_NF];
     float unc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    if (!invert(Ha, n, Cv)) {
+    bool inverted = false;
+    if (n == NF) {  // every block free: symmetric positive definite in all but degenerate cases -> registers only
+      float Hs[NF][NF], Ci[NF][NF];
+#pragma unroll
+      for (int i = 0; i < NF; i++)
+#pragma unroll
+        for (int j = 0; j < NF; j++) Hs[i][j] = Hf[i][j];
+      inverted = spd_inverse_fixed<NF>(Hs, Ci);
+      if (inverted) {
+#pragma unroll
+        for (int i = 0; i < NF; i++)
+#pragma unroll
+          for (int j = 0; j < NF; j++) Cv[i * NF + j] = Ci[i][j];
+      }
+    }
+    if (!inverted && !invert(Ha, n, Cv)) {
       fl |= GCLM_STATUS_COV_SINGULAR;
       for (int i = 0; i < n * n; i++) Cv[i] = __int_as_float(0x7fc00000);
     }
@@ -322,6 +344,7 @@ __device__ __noinline__ void lm_step_image(const PassArgs& a, const PassId pid, 
     finalize_image<MODEL>(a, b, sums, st);  // st.P: the final estimate (the prologue applied the stop rule)
     return;
   }
+  GCLM_SOLVER_STAMP(0);
   const float invN = 1.f / ((float)a.H * (float)a.Wt);
   const float cu = sums[NH + NF] * (a.up_scale * a.up_scale) * invN;
   const float cl = sums[NH + NF + 1] * (a.lat_scale * a.lat_scale) * invN;
@@ -329,6 +352,7 @@ __device__ __noinline__ void lm_step_image(const PassArgs& a, const PassId pid, 
   float lam = st.lam;
   bool converged = false;
   if (pid.pass == 0) {
+    if (a.fused_init) { a.flags[b] = 0u; a.stop_at[b] = a.num_steps; }  // what lm_init_kernel would have set
     a.cost0[b * 3] = cost; a.cost0[b * 3 + 1] = cu; a.cost0[b * 3 + 2] = cl;
   } else {
     // this pass evaluated cost(theta_i) == "new_cost" of iteration i-1 (lm_optimizer.py:607-613)
@@ -350,60 +374,73 @@ __device__ __noinline__ void lm_step_image(const PassArgs& a, const PassId pid, 
   // ---- optimizer_step (lm_optimizer.py:109-137) on the active columns ----
   int act[NF];
   const int n = active_columns(MODEL, a.est_gravity, a.est_focal, act);
-  float Hf[NF][NF];
-  {
-    int idx = 0;
-    for (int i = 0; i < NF; i++)
-      for (int j = i; j < NF; j++) { Hf[i][j] = sums[idx]; Hf[j][i] = sums[idx]; idx++; }
-  }
-  float d[MAX_NF];
+  // the step, by block: gravity (d0, d1), focal (dfo), distortion (dk)
+  float d0 = 0.f, d1 = 0.f, dfo = 0.f, dk[2] = {0.f, 0.f};
   bool solved;
-  if (n == NF) {  // every block is free (the common case): compile-time size, all in registers
+  if (n == NF) {  // every block is free (the common case): compile-time size and indices, all in registers
     float Af[NF][NF], df[NF];
+    {
+      int idx = 0;
 #pragma unroll
-    for (int i = 0; i < NF; i++) {
-      df[i] = sums[NH + i];
+      for (int i = 0; i < NF; i++) {
+        df[i] = sums[NH + i];
 #pragma unroll
-      for (int j = 0; j < NF; j++) Af[i][j] = Hf[i][j];
+        for (int j = i; j < NF; j++) { Af[i][j] = sums[idx]; Af[j][i] = sums[idx]; idx++; }
+      }
     }
 #pragma unroll
     for (int i = 0; i < NF; i++) Af[i][i] += fmaxf(Af[i][i] * lam, 1e-6f);
     solved = cholesky_solve_fixed<NF>(Af, df);
-#pragma unroll
-    for (int i = 0; i < NF; i++) d[i] = df[i];
+    if (solved) {
+      d0 = df[0]; d1 = df[1]; dfo = df[2];
+      if constexpr (K > 0) dk[0] = df[3];
+      if constexpr (K > 1) dk[1] = df[4];
+    }
   } else {
-    float A[MAX_NF * MAX_NF];
+    float Hf[NF][NF];
+    {
+      int idx = 0;
+      for (int i = 0; i < NF; i++)
+        for (int j = i; j < NF; j++) { Hf[i][j] = sums[idx]; Hf[j][i] = sums[idx]; idx++; }
+    }
+    float A[MAX_NF * MAX_NF], d[MAX_NF];
     for (int i = 0; i < n; i++) {
       d[i] = sums[NH + act[i]];
       for (int j = 0; j < n; j++) A[i * n + j] = Hf[act[i]][act[j]];
     }
     for (int i = 0; i < n; i++) A[i * n + i] += fmaxf(A[i * n + i] * lam, 1e-6f);
     solved = cholesky(A, n);
-    if (solved) cholesky_solve(A, n, d);
+    if (solved) {
+      cholesky_solve(A, n, d);
+      int o = 0;
+      if (a.est_gravity) { d0 = d[0]; d1 = d[1]; o = 2; }
+      if (a.est_focal) dfo = d[o++];
+      for (int k = 0; k < K; k++) dk[k] = d[o + k];
+    }
   }
-  if (!solved) {
-    for (int i = 0; i < n; i++) d[i] = 0.f;
-    a.flags[b] |= GCLM_STATUS_CHOLESKY_FAILED;
-  }
+  GCLM_SOLVER_STAMP(1);
+  if (!solved) a.flags[b] |= GCLM_STATUS_CHOLESKY_FAILED;  // zero step for this image (lm_optimizer.py:129-133)
   // ---- update_estimate (lm_optimizer.py:518-549) into the other parameter buffer ----
   const float* Pc = st.P;
   float* Pn = a.P + ((size_t)b * 2 + (sl ^ 1)) * PSTRIDE;
   float cam[8], g[3];
+#pragma unroll
   for (int i = 0; i < 8; i++) cam[i] = Pc[i];
+#pragma unroll
   for (int i = 0; i < 3; i++) g[i] = Pc[8 + i];
-  int o = 0;
-  float d0 = 0.f, d1 = 0.f, df = 0.f;
-  if (a.est_gravity) { d0 = d[0]; d1 = d[1]; o = 2; }
   gravity_update(g, d0, d1, a.spherical);
-  if (a.est_focal) df = d[o++];
-  focal_update(cam, df, a.log_focal);
-  if (K > 0 && a.est_dist) dist_update(MODEL, cam, d + o);
+  GCLM_SOLVER_STAMP(2);
+  focal_update(cam, dfo, a.log_focal);
+  if (K > 0 && a.est_dist) dist_update(MODEL, cam, dk);
+  GCLM_SOLVER_STAMP(3);
   for (int i = 0; i < 8; i++) Pn[i] = cam[i];
   for (int i = 0; i < 3; i++) Pn[8 + i] = g[i];
   a.slot[b] = sl ^ 1;
+  GCLM_SOLVER_STAMP(4);
   if (a.stop_mode == GCLM_STOP_BATCH) {
     if (pid.pass >= 1) batch_stop_vote(a, pid, converged);
   }
+  GCLM_SOLVER_STAMP(5);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -569,19 +606,19 @@ __device__ __forceinline__ void shared_update_image(const PassArgs& a, int b, co
     if (ok) cholesky_solve(S, ni, rhs);
   }
   if (!ok) for (int i = 0; i < 3; i++) rhs[i] = 0.f;  // zero step for everybody (:129-133)
-  const float* sc = a.schur + (size_t)b * SCHUR_STRIDE;
+  const float* sc = a.schur + (size_t)b * SCHUR_STRIDE;  // written by another CTA of THIS launch: read through L2
   float d0 = 0.f, d1 = 0.f;
   if (ng == 2 && ok) {
-    d0 = sc[31]; d1 = sc[32];
-    for (int j = 0; j < ni; j++) { d0 -= sc[25 + j] * rhs[j]; d1 -= sc[28 + j] * rhs[j]; }
+    d0 = __ldcg(sc + 31); d1 = __ldcg(sc + 32);
+    for (int j = 0; j < ni; j++) { d0 -= __ldcg(sc + 25 + j) * rhs[j]; d1 -= __ldcg(sc + 28 + j) * rhs[j]; }
   }
   if (!ok) a.flags[b] |= GCLM_STATUS_CHOLESKY_FAILED;
-  const int sl = a.slot[b];
+  const int sl = __ldcg(&a.slot[b]);
   const float* Pc = a.P + ((size_t)b * 2 + sl) * PSTRIDE;
   float* Pn = a.P + ((size_t)b * 2 + (sl ^ 1)) * PSTRIDE;
   float cam[8], g[3];
-  for (int i = 0; i < 8; i++) cam[i] = Pc[i];
-  for (int i = 0; i < 3; i++) g[i] = Pc[8 + i];
+  for (int i = 0; i < 8; i++) cam[i] = __ldcg(Pc + i);
+  for (int i = 0; i < 3; i++) g[i] = __ldcg(Pc + 8 + i);
   gravity_update(g, d0, d1, a.spherical);
   int o = 0;
   float df = 0.f;
@@ -706,22 +743,33 @@ __device__ __forceinline__ void
   if (threadIdx.x == 0) {
     // everything this CTA (and, if it turns out to be the image's last one, its solver) needs to know about the
     // image: independent L2 loads, ONE round trip (both parameter buffers are fetched, the slot picks one)
-    const int stop = __ldcg(&a.ctrl->stop);
-    const int sl0 = __ldcg(&a.slot[b]);
-    const unsigned fl = __ldcg(&a.flags[b]);
-    const float lam = __ldcg(&a.lam[b]), prev = __ldcg(&a.prev_cost[b]);
-    const float4* P4 = reinterpret_cast<const float4*>(a.P + (size_t)b * 2 * PSTRIDE);
-    float4 q[6];
+    int skip = 0;
+    if (a.fused_init && pid.pass == 0 && !pid.is_final) {
+      // first pass of the persistent schedule with the set-up folded in: the state lm_init_kernel would have
+      // written, straight from the caller's initial estimate (Gravity.__init__ normalises, gravity.py:26)
+      for (int i = 0; i < 8; i++) s_img.P[i] = a.cam0[(size_t)b * 8 + i];
+      float g[3] = {a.g0[(size_t)b * 3], a.g0[(size_t)b * 3 + 1], a.g0[(size_t)b * 3 + 2]};
+      normalize3(g);
+      s_img.P[8] = g[0]; s_img.P[9] = g[1]; s_img.P[10] = g[2]; s_img.P[11] = 0.f;
+      s_img.lam = a.lambda0; s_img.prev_cost = 0.f; s_img.slot = 0; s_img.flags = 0u;
+    } else {
+      const int stop = __ldcg(&a.ctrl->stop);
+      const int sl0 = __ldcg(&a.slot[b]);
+      const unsigned fl = __ldcg(&a.flags[b]);
+      const float lam = __ldcg(&a.lam[b]), prev = __ldcg(&a.prev_cost[b]);
+      const float4* P4 = reinterpret_cast<const float4*>(a.P + (size_t)b * 2 * PSTRIDE);
+      float4 q[6];
 #pragma unroll
-    for (int i = 0; i < 6; i++) q[i] = __ldcg(P4 + i);
-    int sl = sl0;
-    if (pid.is_final && stop) sl ^= 1;  // batch stop fired: the tentative update of that pass is dropped
-    const float4 p0 = sl ? q[3] : q[0], p1 = sl ? q[4] : q[1], p2 = sl ? q[5] : q[2];
-    s_img.P[0] = p0.x; s_img.P[1] = p0.y; s_img.P[2] = p0.z; s_img.P[3] = p0.w;
-    s_img.P[4] = p1.x; s_img.P[5] = p1.y; s_img.P[6] = p1.z; s_img.P[7] = p1.w;
-    s_img.P[8] = p2.x; s_img.P[9] = p2.y; s_img.P[10] = p2.z; s_img.P[11] = p2.w;
-    s_img.lam = lam; s_img.prev_cost = prev; s_img.slot = sl0; s_img.flags = fl;
-    const int skip = !pid.is_final && (stop || (fl & FLAG_FROZEN));
+      for (int i = 0; i < 6; i++) q[i] = __ldcg(P4 + i);
+      int sl = sl0;
+      if (pid.is_final && stop) sl ^= 1;  // batch stop fired: the tentative update of that pass is dropped
+      const float4 p0 = sl ? q[3] : q[0], p1 = sl ? q[4] : q[1], p2 = sl ? q[5] : q[2];
+      s_img.P[0] = p0.x; s_img.P[1] = p0.y; s_img.P[2] = p0.z; s_img.P[3] = p0.w;
+      s_img.P[4] = p1.x; s_img.P[5] = p1.y; s_img.P[6] = p1.z; s_img.P[7] = p1.w;
+      s_img.P[8] = p2.x; s_img.P[9] = p2.y; s_img.P[10] = p2.z; s_img.P[11] = p2.w;
+      s_img.lam = lam; s_img.prev_cost = prev; s_img.slot = sl0; s_img.flags = fl;
+      skip = !pid.is_final && (stop || (fl & FLAG_FROZEN));
+    }
     s_skip = skip;
     if (!skip) {
       make_pass_const(s_img.P, s_img.P + 8, a.spherical != 0, a.log_focal != 0, pid.is_final != 0 && a.final_rpf != 0, s_pc);
@@ -1040,18 +1088,45 @@ __device__ __forceinline__ void
     if (!s_last) return;
     GCLM_STAMP(4);
     __threadfence();
-    if (threadIdx.x < NACC) {  // deterministic: tile order, independent of arrival order
-      float s = 0.f;
-      const float* p = a.partials + (size_t)b * S * NACC + threadIdx.x;
-      int t = 0;
-      for (; t + 8 <= S; t += 8) {  // 8 independent loads in flight, added in tile order
+    // deterministic: tile order, independent of arrival order.  All S x NACC partials are fetched by the whole
+    // CTA at once (one L2 round trip) into the idle ring memory when they fit, then added in order.
+    const float* p = a.partials + (size_t)b * S * NACC;
+    float* stage = reinterpret_cast<float*>(dyn_smem);
+    const bool staged = FULL && (size_t)S * NACC * sizeof(float) <= (size_t)RING_STAGES * 5 * blockDim.x * (C16 ? 12 : 16);
+    if (staged) {
+      const int total = S * NACC;
+      for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {  // 8 loads in flight per thread, then the stores
         float x[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) x[k] = __ldcg(p + (size_t)(t + k) * NACC);
+        for (int k = 0; k < 8; k++) { const int i = i0 + k * blockDim.x; x[k] = i < total ? __ldcg(p + i) : 0.f; }
 #pragma unroll
-        for (int k = 0; k < 8; k++) s += x[k];
+        for (int k = 0; k < 8; k++) { const int i = i0 + k * blockDim.x; if (i < total) stage[i] = x[k]; }
       }
-      for (; t < S; t++) s += __ldcg(p + (size_t)t * NACC);
+      __syncthreads();
+    }
+    if (threadIdx.x < NACC) {
+      float s = 0.f;
+      if (staged) {
+        int t = 0;
+        for (; t + 8 <= S; t += 8) {  // loads first (in-order core: a load per add would serialise on LDS latency)
+          float x[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) x[k] = stage[(t + k) * NACC + threadIdx.x];
+#pragma unroll
+          for (int k = 0; k < 8; k++) s += x[k];
+        }
+        for (; t < S; t++) s += stage[t * NACC + threadIdx.x];
+      } else {
+        int t = 0;
+        for (; t + 8 <= S; t += 8) {  // 8 independent loads in flight, added in tile order
+          float x[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) x[k] = __ldcg(p + (size_t)(t + k) * NACC + threadIdx.x);
+#pragma unroll
+          for (int k = 0; k < 8; k++) s += x[k];
+        }
+        for (; t < S; t++) s += __ldcg(p + (size_t)t * NACC + threadIdx.x);
+      }
       s_sum[threadIdx.x] = s;
     }
     __syncthreads();
@@ -1090,19 +1165,28 @@ __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MO
 }
 #endif
 
-// Grid-wide barrier of the persistent kernel (all CTAs are co-resident: cooperative launch).  Arrivals are
-// counted monotonically within a solve (lm_init_kernel zeroes the counter), so no reset race exists.
-__device__ __forceinline__ void grid_barrier(Ctrl* c, unsigned target) {
+// Grid-wide barrier of the persistent kernel (all CTAs are co-resident: cooperative launch).  Sense reversal:
+// the last arriver zeroes the count and bumps the generation, the others wait for the generation to move.
+// No per-solve reset is needed (count is 0 between barriers), so a captured launch can be replayed.
+__device__ __forceinline__ void grid_barrier(Ctrl* c, unsigned& my_gen) {
   __syncthreads();
   if (threadIdx.x == 0) {
     __threadfence();
-    atomicAdd(&c->bar, 1u);
-    unsigned v;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&c->bar) : "memory");
-    } while (v < target);
+    if (atomicAdd(&c->bar_count, 1u) == gridDim.x - 1u) {
+      c->bar_count = 0u;
+      __threadfence();
+      atomicAdd(&c->bar_gen, 1u);
+    } else {
+      unsigned v;
+      unsigned long long spins = 0;
+      do {
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&c->bar_gen) : "memory");
+        if (++spins > (1ull << 27)) { c->comm_error = 2; break; }  // never hang the device: flag and fall through
+      } while (v == my_gen);
+    }
     __threadfence();
   }
+  my_gen++;
   __syncthreads();
 }
 
@@ -1115,11 +1199,34 @@ __device__ __forceinline__ void grid_barrier(Ctrl* c, unsigned target) {
 template <int MODEL, bool GEN_D, bool FULL, bool PACK>
 __global__ void __launch_bounds__(Tune<MODEL, PACK>::MAX_WARPS_CTA * 32, Tune<MODEL, PACK>::MIN_BLOCKS)
     lm_persistent_kernel(const __grid_constant__ PassArgs a) {
-  unsigned target = 0;
+  // every CTA reads the generation before it can possibly move (no barrier completes without this CTA)
+  unsigned gen = 0;
+  if (threadIdx.x == 0) asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(&a.ctrl->bar_gen) : "memory");
+  if (a.fused_init) {
+    // set-up folded in: batch control block (read by others only after the first barrier) ...
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      a.ctrl->stop = 0; a.ctrl->stop_at = a.num_steps;
+      a.ctrl->vote[0] = a.ctrl->vote[1] = 0ull;
+      a.ctrl->img_done = 0u; a.ctrl->comm_error = 0;
+    }
+    // ... and sin(latitude) of THIS CTA's tile (the only part of the plane it will ever read)
+    const int b = blockIdx.x / a.tiles_per_image, tile = blockIdx.x - b * a.tiles_per_image;
+    const int y0 = tile * a.rows_per_tile, y1 = min(a.H, y0 + a.rows_per_tile);
+    const size_t base = ((size_t)b * a.H + y0) * a.W;
+    const int n4 = (y1 - y0) * a.W / 4;
+    const float4* in = reinterpret_cast<const float4*>(a.lat_raw + base);
+    float4* out = reinterpret_cast<float4*>(const_cast<float*>(a.lat) + base);
+    for (int i = threadIdx.x; i < n4; i += blockDim.x) {
+      float4 x = in[i];
+      x.x = sinf(x.x); x.y = sinf(x.y); x.z = sinf(x.z); x.w = sinf(x.w);
+      out[i] = x;
+    }
+    __threadfence();
+    __syncthreads();
+  }
   for (int p = 0; p < a.num_steps; ++p) {
     pass_body<MODEL, GEN_D, FULL ? 1 : 0, PACK>(a, PassId{p, 0});
-    target += gridDim.x;
-    grid_barrier(a.ctrl, target);
+    grid_barrier(a.ctrl, gen);
 #ifdef GCLM_PHASE_TIMERS
     if (threadIdx.x == 0 && a.dbg) a.dbg[((size_t)p * gridDim.x + blockIdx.x) * 8 + 7] = clock64();
 #endif
@@ -1136,7 +1243,7 @@ __global__ void lm_init_kernel(PassArgs a, const float* cam0, const float* g0) {
   if (b == 0) {
     a.ctrl->stop = 0; a.ctrl->stop_at = a.num_steps;
     a.ctrl->vote[0] = a.ctrl->vote[1] = 0ull;
-    a.ctrl->img_done = 0u; a.ctrl->comm_error = 0; a.ctrl->bar = 0u;
+    a.ctrl->img_done = 0u; a.ctrl->comm_error = 0;
   }
   if (b >= a.B) return;
   float* P0 = a.P + (size_t)b * 2 * PSTRIDE;
@@ -1335,7 +1442,8 @@ struct gclm_handle {
   // the per-device handle ([model][gen_d][full][pack])
   size_t smem_configured[4][2][3][2] = {};
   size_t smem_configured_persistent[4][2][2][2] = {};
-  int persistent_blocks_per_sm[4][2][2][2] = {};  // occupancy of lm_persistent_kernel (0 = not queried yet)
+  int persistent_blocks_per_sm[4][2][2][2] = {};  // occupancy of lm_persistent_kernel (0 = not queried yet) ...
+  unsigned persistent_block_threads[4][2][2][2] = {};  // ... for this block size
 #ifdef GCLM_TMA2D
   gclm::TmaMaps maps;  // tensor maps of the current solve
 #endif
@@ -1347,6 +1455,12 @@ struct gclm_handle {
   int64_t tcount = 0;
   char last_error[256] = {0};
   long long* dbg = nullptr;  // GCLM_PHASE_TIMERS build only
+  size_t ctrl_offset = 0;    // where the control block of the last solve lives in scratch (gclm_debug_ctrl)
+  // The persistent schedule relies on tickets[] and the barrier words being 0 when it starts (every pass and
+  // every barrier leaves them 0).  Their place in the scratch block moves with the batch size, so whenever the
+  // layout differs from the one last zeroed, that region is cleared on the stream first.
+  size_t zeroed_tickets_off = (size_t)-1, zeroed_ctrl_off = (size_t)-1;
+  int zeroed_batch = -1;
 };
 
 // Event pair around the pass launches of one solve (only when timing is on; never while capturing).
@@ -1470,10 +1584,16 @@ TileCfg tile_config(int B, int H, int W, int num_sms, int rows_override, int max
   // for any image width.
   TileCfg t;
   const int NS = (W + 127) / 128;
-  int g = NS, r = max_warps;
-  while (r) { const int q = g % r; g = r; r = q; }  // gcd(NS, max_warps)
-  t.nwarps = max_warps;
-  t.rsub = max_warps / g;
+  int nw = max_warps;
+  // tiny batches (a handful of images: the calibrate() case) are latency-bound and leave most SMs idle: a warp
+  // count that is a multiple of the strip count gives every warp ONE job, so that a tile can be as small as
+  // rsub rows and each warp computes a single row per pass
+  const bool tiny = rows_override <= 0 && (int64_t)B * ((H + 7) / 8) < num_sms && NS <= max_warps;
+  if (tiny) nw = (max_warps / NS) * NS;
+  int g = NS, r = nw;
+  while (r) { const int q = g % r; g = r; r = q; }  // gcd(NS, nw)
+  t.nwarps = nw;
+  t.rsub = nw / g;
   const int jobs_per_warp = NS / g;
   // ~120 rows walked by a warp per tile (long tiles amortise the CTA prologue/epilogue), tiles of
   // equal height
@@ -1486,7 +1606,7 @@ TileCfg tile_config(int B, int H, int W, int num_sms, int rows_override, int max
     while (rj >= 8 && (int64_t)B * ((H + rj * t.rsub - 1) / (rj * t.rsub)) < 12ll * num_sms) rj /= 2;  // stays >= 4
     // tiny batches (a handful of images: the calibrate() case) are latency-bound: as many CTAs as the image
     // allows, down to single-row jobs (rows_per_tile stays >= 4, which is what gclm_reserve sizes for)
-    while (rj >= 2 && (rj / 2) * t.rsub >= 4 && (int64_t)B * ((H + rj * t.rsub - 1) / (rj * t.rsub)) < num_sms / 2) rj /= 2;
+    while (rj >= 2 && (rj / 2) * t.rsub >= (tiny ? 2 : 4) && (int64_t)B * ((H + rj * t.rsub - 1) / (rj * t.rsub)) < num_sms / 2) rj /= 2;
   }
   t.rows_per_tile = rj * t.rsub;
   t.tiles_per_image = (H + t.rows_per_tile - 1) / t.rows_per_tile;
@@ -1520,13 +1640,17 @@ int ensure_scratch(gclm_handle* h, size_t bytes) {
   if (h->scratch) cudaFree(h->scratch);
   h->scratch = nullptr; h->scratch_bytes = 0;
   CUDA_TRY(h, cudaMalloc(&h->scratch, bytes));
+  // tickets and the persistent kernel's barrier words rely on starting at 0 (every pass / barrier leaves them 0)
+  CUDA_TRY(h, cudaMemset(h->scratch, 0, std::min<size_t>(bytes, (size_t)64 << 20)));
   h->scratch_bytes = bytes;
+  h->zeroed_batch = -1;
   return GCLM_OK;
 }
 
-int max_tiles_for(int H, int W) {
-  (void)W;
-  return (H + 3) / 4 + 1;  // smallest auto tile is 4 rows (rsub == 1)
+int max_tiles_for(int B, int H, int num_sms) {
+  // smallest tile tile_config can choose or the caller can ask for: 2 rows for tiny batches, 4 rows otherwise
+  const bool tiny = (int64_t)B * ((H + 7) / 8) < num_sms;
+  return tiny ? (H + 1) / 2 + 1 : (H + 3) / 4 + 1;
 }
 
 #ifdef GCLM_TMA2D
@@ -1611,6 +1735,8 @@ bool launch_persistent_one(gclm_handle* h, const PassArgs& a, dim3 grid, dim3 bl
     h->persistent_blocks_per_sm[MODEL][GEN_D][FULL][PACK] = 0;
   }
   int& per_sm = h->persistent_blocks_per_sm[MODEL][GEN_D][FULL][PACK];
+  unsigned& for_threads = h->persistent_block_threads[MODEL][GEN_D][FULL][PACK];
+  if (for_threads != block.x) { per_sm = 0; for_threads = block.x; }  // tiny batches use other warp counts
   if (per_sm == 0) {
     int nb = 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, (int)block.x, smem) != cudaSuccess) { cudaGetLastError(); nb = -1; }
@@ -1635,6 +1761,16 @@ bool launch_persistent_model(gclm_handle* h, const PassArgs& a, bool gen_d, bool
               : launch_persistent_one<MODEL, false, false, PACK>(h, a, grid, block, 0, s);
 }
 #endif
+
+// tickets[] .. end of the control block start at 0 for the persistent schedule (see gclm_handle)
+void ensure_persistent_state_zero(gclm_handle* h, const Layout& L, int batch, cudaStream_t s) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  const bool capturing = cudaStreamIsCapturing(s, &cs) == cudaSuccess && cs != cudaStreamCaptureStatusNone;
+  const bool known = h->zeroed_tickets_off == L.tickets && h->zeroed_ctrl_off == L.ctrl && h->zeroed_batch == batch;
+  if (known && !capturing) return;
+  cudaMemsetAsync(static_cast<char*>(h->scratch) + L.tickets, 0, L.ctrl + sizeof(Ctrl) - L.tickets, s);
+  if (!capturing) { h->zeroed_tickets_off = L.tickets; h->zeroed_ctrl_off = L.ctrl; h->zeroed_batch = batch; }
+}
 
 // Small grids only (GCLM_PERSISTENT=0 disables): a few hundred CTAs that are all resident at once.
 bool launch_persistent(gclm_handle* h, const PassArgs& a, bool gen_d, bool full, dim3 grid, dim3 block, cudaStream_t s) {
@@ -1737,6 +1873,8 @@ PassArgs make_args(gclm_handle* h, const gclm_problem* p, const gclm_options* o,
   a.stop_at = reinterpret_cast<int*>(base + L.stop_at);
   a.tickets = reinterpret_cast<unsigned*>(base + L.tickets);
   a.ctrl = reinterpret_cast<Ctrl*>(base + L.ctrl);
+  h->ctrl_offset = L.ctrl;
+  if (p->batch != h->zeroed_batch) h->zeroed_batch = -1;  // another layout is about to write over that region
   a.partials = reinterpret_cast<float*>(base + L.partials);
   a.schur = reinterpret_cast<float*>(base + L.schur);
   a.res = *r;
@@ -1843,12 +1981,19 @@ int gclm_reserve(gclm_handle* h, int batch, int height, int width) {
   if (!guard.ok()) return GCLM_ERR_CUDA;
   std::lock_guard<std::mutex> lk(h->mu);
   if (h->have_last) cudaEventSynchronize(h->last_done);  // never free scratch a queued solve still uses
-  const Layout L = make_layout(batch, max_tiles_for(height, width), (size_t)height * padded_width(width), width % 4 != 0);
+  const Layout L = make_layout(batch, max_tiles_for(batch, height, h->num_sms), (size_t)height * padded_width(width), width % 4 != 0);
   return ensure_scratch(h, L.total);
 }
 
 int64_t gclm_launch_count(const gclm_handle* h) { return h ? h->launches : 0; }
 int64_t gclm_persistent_count(const gclm_handle* h) { return h ? h->persistent_solves : 0; }
+// debug: raw copy of the device control block (stop, stop_at, vote[2] as 4 words, img_done, comm_error, bar_count, bar_gen)
+int gclm_debug_ctrl(gclm_handle* h, int32_t out[10]) {
+  if (!h || !h->scratch || !out) return GCLM_ERR_INVALID_ARGUMENT;
+  cudaDeviceSynchronize();
+  const size_t off = h->ctrl_offset;
+  return cudaMemcpy(out, static_cast<char*>(h->scratch) + off, sizeof(int32_t) * 10, cudaMemcpyDeviceToHost) == cudaSuccess ? GCLM_OK : GCLM_ERR_CUDA;
+}
 #ifdef GCLM_PHASE_TIMERS
 int gclm_debug_stamps(gclm_handle* h, long long* out, int n) {  // debug build: copy the first n stamps to the host
   if (!h || !h->dbg) return -1;
@@ -1864,7 +2009,7 @@ int gclm_tile_config(int batch, int height, int width, int camera_model, int num
   const TileCfg t = tile_config(batch, height, padded_width(width), num_sms, rows_per_tile,
                                 max_warps_for(camera_model, use_packed()));
   out[0] = t.nwarps; out[1] = t.rsub; out[2] = t.rows_per_tile; out[3] = t.tiles_per_image;
-  out[4] = max_tiles_for(height, width);
+  out[4] = max_tiles_for(batch, height, num_sms);
   return GCLM_OK;
 }
 
@@ -1902,19 +2047,31 @@ static int solve_impl(gclm_handle* h, const gclm_problem* prob, const gclm_optio
   SolveOrder order(h, s);
   const TileCfg t = tile_config(prob->batch, prob->height, padded_width(prob->width), h->num_sms, opt->rows_per_tile,
                                 max_warps_for(prob->camera_model, use_packed()));
-  const Layout L = make_layout(prob->batch, std::max(t.tiles_per_image, max_tiles_for(prob->height, prob->width)),
+  const Layout L = make_layout(prob->batch, std::max(t.tiles_per_image, max_tiles_for(prob->batch, prob->height, h->num_sms)),
                                (size_t)prob->height * padded_width(prob->width), !packed && needs_repack(prob));
   st = ensure_scratch(h, L.total);
   if (st != GCLM_OK) return st;
   PassArgs a = make_args(h, prob, opt, res, t, L, packed);
   const bool full = a.up && a.lat && a.uconf && a.lconf;
+  const dim3 grid((unsigned)((size_t)prob->batch * t.tiles_per_image)), block(t.nwarps * 32);
+  // small batch (the calibrate() case): every pass in ONE cooperative launch, a grid barrier between passes;
+  // with all five planes in place even the set-up (initial state, sin(latitude)) happens inside that launch
+  const bool want_persistent = opt->schedule != GCLM_SCHEDULE_PER_PASS && opt->num_steps >= 1 && !a.conf16;
+  bool launched = false;
+  static int fuse_setup = -1;  // GCLM_FUSED_INIT=0: keep lm_init_kernel / sin_plane_kernel as separate launches (debug knob)
+  if (fuse_setup < 0) { const char* e = getenv("GCLM_FUSED_INIT"); fuse_setup = (e && e[0] == '0') ? 0 : 1; }
+  if (want_persistent && (int64_t)grid.x <= 4ll * h->num_sms) ensure_persistent_state_zero(h, L, prob->batch, s);
+  if (want_persistent && fuse_setup && full && !packed && !needs_repack(prob)) {
+    a.fused_init = 1; a.cam0 = prob->camera_init; a.g0 = prob->gravity_init; a.lat_raw = prob->latitude_field;
+    PassTimer timer(h, s, opt->num_steps + 1);
+    launched = launch_persistent(h, a, !opt->use_log_focal, full, grid, block, s);
+    if (launched) { h->launches++; h->persistent_solves++; timer.stop(); order.done(); CUDA_TRY(h, cudaGetLastError()); return GCLM_OK; }
+    a.fused_init = 0;
+  }
   lm_init_kernel<<<(prob->batch + 127) / 128, 128, 0, s>>>(a, prob->camera_init, prob->gravity_init);
   h->launches++;
   if (!packed) launch_sin_plane(h, prob, a, s);  // packed fields already hold sin(latitude)
-  const dim3 grid((unsigned)((size_t)prob->batch * t.tiles_per_image)), block(t.nwarps * 32);
   PassTimer timer(h, s, opt->num_steps + 1);
-  // small batch (the calibrate() case): every pass in ONE cooperative launch, a grid barrier between passes
-  const bool want_persistent = opt->schedule != GCLM_SCHEDULE_PER_PASS && opt->num_steps >= 1 && !a.conf16;
   if (want_persistent && launch_persistent(h, a, !opt->use_log_focal, full, grid, block, s)) {
     h->launches++;
     h->persistent_solves++;
@@ -2027,7 +2184,7 @@ int gclm_system(gclm_handle* h, const gclm_problem* prob, const gclm_options* op
   SolveOrder order(h, s);
   const TileCfg t = tile_config(prob->batch, prob->height, padded_width(prob->width), h->num_sms, opt->rows_per_tile,
                                 max_warps_for(prob->camera_model, use_packed()));
-  const Layout L = make_layout(prob->batch, std::max(t.tiles_per_image, max_tiles_for(prob->height, prob->width)),
+  const Layout L = make_layout(prob->batch, std::max(t.tiles_per_image, max_tiles_for(prob->batch, prob->height, h->num_sms)),
                                (size_t)prob->height * padded_width(prob->width), needs_repack(prob));
   st = ensure_scratch(h, L.total);
   if (st != GCLM_OK) return st;
@@ -2065,7 +2222,7 @@ int gclm_solve_shared(gclm_handle* h, const gclm_problem* prob, const gclm_optio
   SolveOrder order(h, s);
   const TileCfg t = tile_config(prob->batch, prob->height, padded_width(prob->width), h->num_sms, opt->rows_per_tile,
                                 max_warps_for(prob->camera_model, use_packed()));
-  const Layout L = make_layout(prob->batch, std::max(t.tiles_per_image, max_tiles_for(prob->height, prob->width)),
+  const Layout L = make_layout(prob->batch, std::max(t.tiles_per_image, max_tiles_for(prob->batch, prob->height, h->num_sms)),
                                (size_t)prob->height * padded_width(prob->width), needs_repack(prob));
   st = ensure_scratch(h, L.total);
   if (st != GCLM_OK) return st;

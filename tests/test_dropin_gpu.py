@@ -119,7 +119,7 @@ def test_calibrate_single_image_through_the_reference_extractor(extractor, camer
         l0 = eng.launch_count
         res = ex.calibrate(img, camera_model=camera_model)
         torch.cuda.synchronize()
-        assert eng.launch_count - l0 >= 3 and eng.launch_count > l0, "the engine did not run"  # B = 1: persistent schedule
+        assert eng.launch_count > l0 and eng.persistent_count > 0, "the engine did not run"  # B = 1: ONE cooperative launch
         compare(res, ref, K)
         assert abs(float(res["camera"].f[0, 1]) / (330.0 * 480 / 320) - 1) < 0.25  # undo_scale_crop applied
     finally:

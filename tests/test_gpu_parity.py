@@ -729,7 +729,7 @@ def test_persistent_schedule_is_bit_identical_to_per_pass(dev, model, B, h, w):
         torch.cuda.synchronize()
         if sched.startswith("persistent"):
             assert eng.persistent_count == n0 + 1
-            assert eng.launch_count - l0 == 3  # initial estimate, sin(latitude) plane, the persistent kernel
+            assert eng.launch_count - l0 == 1  # set-up, all passes and the solver: ONE cooperative launch
         else:
             assert eng.persistent_count == n0 and eng.launch_count - l0 == 2 + 11
     a, b = outs["per_pass"], outs["persistent"]

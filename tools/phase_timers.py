@@ -22,11 +22,13 @@ torch.cuda.synchronize()
 cfg = (ctypes.c_int32 * 5)()
 eng.lib.gclm_tile_config(B, h, w, 0, 148, rows, cfg)
 ncta = B * cfg[3]
-n = (iters + 1) * ncta * 8
+n = 400000 + (iters + 1) * 8
 buf = (ctypes.c_longlong * n)()
 eng.lib.gclm_debug_stamps.restype = ctypes.c_int
 assert eng.lib.gclm_debug_stamps(eng._h, buf, n) == 0
-st = np.array(buf[:], dtype=np.int64).reshape(iters + 1, ncta, 8)
+allb = np.array(buf[:], dtype=np.int64)
+st = allb[:(iters + 1) * ncta * 8].reshape(iters + 1, ncta, 8)
+sol = allb[400000:400000 + (iters + 1) * 8].reshape(iters + 1, 8)
 mhz = 1965.0
 print(f"tiles {ncta} (rows_per_tile {cfg[2]}, warps {cfg[0]}, rsub {cfg[1]}), schedule {sched}")
 names = ["prologue", "stream", "cta-reduce", "ticket", "sum partials", "solver+vote", "barrier"]
@@ -36,4 +38,7 @@ for p in range(iters + 1):
     last = int(np.argmax(s[:, 4]))
     d = np.diff(s[last, :8].astype(np.float64)) / mhz
     others = (s[:, 3] - s[:, 0]).astype(np.float64) / mhz
+    if p < iters:
+        sd = np.diff(sol[p, :6].astype(np.float64)) / mhz
+        print(f"         solver: cost+lambda+cholesky {sd[0]:.2f}, gravity {sd[1]:.2f}, focal/dist {sd[2]:.2f}, stores {sd[3]:.2f}, vote {sd[4]:.2f}")
     print(f"pass {p:2d}: " + ", ".join(f"{nm} {x:6.2f}" for nm, x in zip(names, d)) + f" | all CTAs start->reduce: median {np.median(others):.2f} max {others.max():.2f} us")
