@@ -18,3 +18,7 @@ for wl in simple_radial_b4096 divisional_b1024 radial_b1024 shared_b2048 pinhole
   python bench.py --workload $wl --steps 10 --warmup 3 --no-cpu --no-e2e 2>/dev/null | tail -1 >> gpurun_out/bench_${T}_models.jsonl
 done
 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_${T}_default.json 2> gpurun_out/bench_${T}_default.err
+timeout 400 python bench.py --impl reference --steps 20 --warmup 5 > gpurun_out/bench_${T}_reference.json 2> gpurun_out/bench_${T}_reference.err
+timeout 120 env GCLM_LIB=$PWD/tools/variants/timers.so python tools/phase_timers.py 0 persistent > gpurun_out/phase_timers_$T.txt 2>&1
+python bench.py --workload pinhole_b1024 --conf16 --steps 10 --warmup 3 --no-cpu --no-e2e --no-shared 2>/dev/null | tail -1 > gpurun_out/bench_${T}_conf16.json
+timeout 300 python -m pytest tests -m gpu -q --timeout 120 --timeout-method thread -p no:cacheprovider 2>&1 | tail -5 > gpurun_out/pytest_$T.log
