@@ -661,7 +661,7 @@ def main():
         shared_rec = {"workload": "shared_b2048", "value": r["value"], "unit": "images/sec", "n_gpus": world,
                       "global_batch": world * swl[1], "ms_per_step": r["ms_per_step"],
                       "frac": r["roofline"]["frac"], "step_frac": r["roofline"]["step_frac"],
-                      "collective": r["collective"], "gpu_launches": r["launches"],
+                      "collective": r["collective"], "gpu_launches": r["launches"], "clocks": r["clocks"],
                       "note": "one focal for all images of all ranks; per LM step one all-reduce of 25 floats, "
                               "done by the last CTA of the pass kernel over NVLink peer memory (p2p-fused) or by "
                               "NCCL; `frac` brackets pass + exchange + update"}

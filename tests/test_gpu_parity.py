@@ -758,3 +758,53 @@ def test_auto_schedule_picks_persistent_only_for_small_grids(dev):
             G.LMOptimizer({"camera_model": "pinhole", "num_steps": 5, "early_stop": False}).eval()(f)
         torch.cuda.synchronize()
         assert eng.persistent_count - n0 == expect
+
+
+def test_solves_on_different_streams_are_ordered(dev):
+    """One handle = one scratch block: a solve enqueued on another stream waits for the previous one (ADVICE r1:
+    two solves under different torch.cuda.stream contexts used to overlap and overwrite each other's state)."""
+    import geocalib_b200 as G
+
+    model, h, w, B = "pinhole", 96, 128, 64
+    cam, grav = synth_params(model, B, h, w, 21)
+    f1 = render_on_device(model, cam, grav, h, w, dev, sigma=0.02, seed=1)
+    cam2, grav2 = synth_params(model, B, h, w, 22)
+    f2 = render_on_device(model, cam2, grav2, h, w, dev, sigma=0.02, seed=2)
+    opt = G.LMOptimizer({"camera_model": model, "num_steps": 12, "early_stop": False}).eval()
+    with torch.no_grad():
+        ref1, ref2 = opt(f1), opt(f2)
+        torch.cuda.synchronize()
+        s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        outs = []
+        for _ in range(3):  # interleave without any host synchronisation in between
+            with torch.cuda.stream(s1):
+                outs.append(("1", opt(f1)))
+            with torch.cuda.stream(s2):
+                outs.append(("2", opt(f2)))
+        torch.cuda.synchronize()
+    for tag, o in outs:
+        ref = ref1 if tag == "1" else ref2
+        assert torch.equal(o["camera"]._data, ref["camera"]._data) and torch.equal(o["gravity"]._data, ref["gravity"]._data)
+
+
+def test_two_devices_in_one_process(dev):
+    """Per-device engines in ONE process (the > 48 KB shared-memory opt-in is a per-device attribute; the
+    entry points must not change the caller's current device)."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (gpurun --gpus 2)")
+    import geocalib_b200 as G
+
+    model, h, w, B = "pinhole", 96, 128, 200  # > 4 x 148 CTAs: the per-pass kernels with the 80 KB ring
+    cam, grav = synth_params(model, B, h, w, 5)
+    outs = []
+    torch.cuda.set_device(0)
+    for d in (0, 1, 0):
+        dd = torch.device("cuda", d)
+        f = render_on_device(model, cam, grav, h, w, dd, sigma=0.02, seed=4)
+        with torch.no_grad():
+            out = G.LMOptimizer({"camera_model": model, "num_steps": 8, "early_stop": False}).eval()(f)
+        torch.cuda.synchronize(dd)
+        assert torch.cuda.current_device() == 0, "the engine changed the caller's current device"
+        assert out["camera"]._data.device == dd and int(out["status"].sum()) == 0
+        outs.append(out["camera"]._data.cpu())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
