@@ -406,7 +406,7 @@ GCLM_HD __forceinline__ Col<V> make_col(const PassConst& pc, V u) {
   return c;
 }
 
-template <int MODEL, bool GEN_D, bool FULL, class V, bool LIT = false, bool K0 = false>
+template <int MODEL, bool GEN_D, bool FULL, class V, bool LIT = false, bool K0 = false, bool UP = true, bool LAT = true>
 GCLM_HD __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMask fm, const Col<V>& col,
                                                  float v, V ox, V oy, V sin_olat, V cu,
                                                  V cl, const RobustConst& rc,
@@ -416,7 +416,8 @@ GCLM_HD __forceinline__ void pixel_accumulate(const PassConst& pc, const FieldMa
   // the masked / literal divisional formulas do not obey the scaling symmetry: their focal row is computed
   // directly and (LIT, k1 != 0) moved into the X basis; K0 means k1 == 0, where X == f
   constexpr bool DIRECT_F = GEN_D || K0 || LIT;
-  const bool has_up = FULL || fm.up, has_lat = FULL || fm.lat;
+  // UP / LAT: compile-time halves of the pixel (a warp may own only the up-field or only the latitude rows)
+  const bool has_up = UP && (FULL || fm.up), has_lat = LAT && (FULL || fm.lat);
   V r2;
   if constexpr (Forms<MODEL>::COLS) r2 = (u * u) + splat<V>(v * v);  // u*u is column-invariant: hoisted out of the row loop
   else r2 = fmaf(u, u, splat<V>(v * v));

@@ -710,6 +710,236 @@ struct Tune {
 };
 inline int max_warps_for(int model, bool pack) { return (model == PINHOLE || !pack) ? GCLM_PIN_WARPS : GCLM_DIST_WARPS; }
 
+// All static shared memory of a CTA in one block, so that the cold parts of a pass (prologue, epilogue) can live
+// in their own __noinline__ functions: the streaming loop's register allocation and instruction schedule then
+// do not depend on what the epilogue happens to contain (measured: unrelated epilogue edits moved the pinhole
+// pass by 6 % through the schedule ptxas picked for the loop).
+template <int NACC>
+struct CtaSmem {
+  PassConst pc;
+  RobustConst rc;
+  ImgState img;
+  float red[MAX_WARPS][NACC];
+  float sum[NACC];
+  float grp[4][NACC];
+  int last, last_img, skip;
+  float part[MAX_WARPS][SCHUR_NSUM + 3];
+  float tot[SCHUR_NSUM + 3];
+};
+
+// Thread 0 of every CTA: the image's state and the constants of this pass.
+template <int MODEL>
+__device__ __noinline__ void cta_prologue(const PassArgs& a, const PassId pid, int b, CtaSmem<Dims<MODEL>::NACC>& sm) {
+    // everything this CTA (and, if it turns out to be the image's last one, its solver) needs to know about the
+    // image: independent L2 loads, ONE round trip (both parameter buffers are fetched, the slot picks one)
+    int skip = 0;
+    if (a.fused_init && pid.pass == 0 && !pid.is_final) {
+      // first pass of the persistent schedule with the set-up folded in: the state lm_init_kernel would have
+      // written, straight from the caller's initial estimate (Gravity.__init__ normalises, gravity.py:26)
+      for (int i = 0; i < 8; i++) sm.img.P[i] = a.cam0[(size_t)b * 8 + i];
+      float g[3] = {a.g0[(size_t)b * 3], a.g0[(size_t)b * 3 + 1], a.g0[(size_t)b * 3 + 2]};
+      normalize3(g);
+      sm.img.P[8] = g[0]; sm.img.P[9] = g[1]; sm.img.P[10] = g[2]; sm.img.P[11] = 0.f;
+      sm.img.lam = a.lambda0; sm.img.prev_cost = 0.f; sm.img.slot = 0; sm.img.flags = 0u;
+    } else {
+      const int stop = __ldcg(&a.ctrl->stop);
+      const int sl0 = __ldcg(&a.slot[b]);
+      const unsigned fl = __ldcg(&a.flags[b]);
+      const float lam = __ldcg(&a.lam[b]), prev = __ldcg(&a.prev_cost[b]);
+      const float4* P4 = reinterpret_cast<const float4*>(a.P + (size_t)b * 2 * PSTRIDE);
+      float4 q[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) q[i] = __ldcg(P4 + i);
+      int sl = sl0;
+      if (pid.is_final && stop) sl ^= 1;  // batch stop fired: the tentative update of that pass is dropped
+      const float4 p0 = sl ? q[3] : q[0], p1 = sl ? q[4] : q[1], p2 = sl ? q[5] : q[2];
+      sm.img.P[0] = p0.x; sm.img.P[1] = p0.y; sm.img.P[2] = p0.z; sm.img.P[3] = p0.w;
+      sm.img.P[4] = p1.x; sm.img.P[5] = p1.y; sm.img.P[6] = p1.z; sm.img.P[7] = p1.w;
+      sm.img.P[8] = p2.x; sm.img.P[9] = p2.y; sm.img.P[10] = p2.z; sm.img.P[11] = p2.w;
+      sm.img.lam = lam; sm.img.prev_cost = prev; sm.img.slot = sl0; sm.img.flags = fl;
+      skip = !pid.is_final && (stop || (fl & FLAG_FROZEN));
+    }
+    sm.skip = skip;
+    if (!skip) {
+      make_pass_const(sm.img.P, sm.img.P + 8, a.spherical != 0, a.log_focal != 0, pid.is_final != 0 && a.final_rpf != 0, sm.pc);
+      sm.rc = make_robust_const(a.up_scale, a.lat_scale);
+    }
+  }
+
+// Everything after the warps have left their per-warp sums in sm.red: tile sum, partials, ticket; in the image's
+// last CTA the ordered sum over the tiles and the solver; in the batch's last CTA the shared-intrinsics tail.
+template <int MODEL, bool GEN_D, int IN>
+__device__ __noinline__ void cta_finish(const PassArgs& a, const PassId pid, int b, int tile, CtaSmem<Dims<MODEL>::NACC>& sm) {
+  constexpr bool FULL = IN != 0, C16 = IN == 2;
+  constexpr int NACC = Dims<MODEL>::NACC;
+  const int nwarps = blockDim.x >> 5;
+  __syncthreads();
+  const int S = a.tiles_per_image;
+  if (threadIdx.x < NACC) {
+    float s = 0.f;
+    for (int w = 0; w < nwarps; w++) s += sm.red[w][threadIdx.x];
+    if (S == 1) sm.sum[threadIdx.x] = s;
+    else { a.partials[((size_t)b * S + tile) * NACC + threadIdx.x] = s; __threadfence(); }
+  }
+  __syncthreads();
+  GCLM_STAMP(3);
+  if (S > 1) {
+    if (threadIdx.x == 0) {
+      const unsigned t = atomicAdd(&a.tickets[b], 1u);
+      sm.last = (t == (unsigned)S - 1u);
+    }
+    __syncthreads();
+    if (!sm.last) return;
+    GCLM_STAMP(4);
+    __threadfence();
+    // deterministic: tile order, independent of arrival order.  All S x NACC partials are fetched by the whole
+    // CTA at once (one L2 round trip) into the idle ring memory when they fit, then added in order.
+    const float* p = a.partials + (size_t)b * S * NACC;
+    extern __shared__ __align__(16) unsigned char dyn_smem_f[];
+    float* stage = reinterpret_cast<float*>(dyn_smem_f);
+    const bool staged = FULL && (size_t)S * NACC * sizeof(float) <= (size_t)RING_STAGES * 5 * blockDim.x * (C16 ? 12 : 16);
+    if (staged) {
+      const int total = S * NACC;
+      for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {  // 8 loads in flight per thread, then the stores
+        float x[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int i = i0 + k * blockDim.x; x[k] = i < total ? __ldcg(p + i) : 0.f; }
+#pragma unroll
+        for (int k = 0; k < 8; k++) { const int i = i0 + k * blockDim.x; if (i < total) stage[i] = x[k]; }
+      }
+      __syncthreads();
+    }
+    // four groups of consecutive tiles are summed concurrently (each in tile order), then the four group sums in
+    // order: a fixed association, identical for every schedule; for S <= 4 it IS the plain sequential sum
+    constexpr int NG = 4;
+    if (threadIdx.x < NG * NACC) {
+      const int g = threadIdx.x / NACC, j = threadIdx.x - g * NACC;
+      const int chunk = (S + NG - 1) / NG;
+      const int t0 = g * chunk, t1 = min(S, t0 + chunk);
+      float s = 0.f;
+      int t = t0;
+      if (staged) {
+        for (; t + 8 <= t1; t += 8) {  // loads first (in-order core: a load per add would serialise on LDS latency)
+          float x[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) x[k] = stage[(t + k) * NACC + j];
+#pragma unroll
+          for (int k = 0; k < 8; k++) s += x[k];
+        }
+        for (; t < t1; t++) s += stage[t * NACC + j];
+      } else {
+        for (; t + 8 <= t1; t += 8) {
+          float x[8];
+#pragma unroll
+          for (int k = 0; k < 8; k++) x[k] = __ldcg(p + (size_t)(t + k) * NACC + j);
+#pragma unroll
+          for (int k = 0; k < 8; k++) s += x[k];
+        }
+        for (; t < t1; t++) s += __ldcg(p + (size_t)t * NACC + j);
+      }
+      sm.grp[g][j] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NACC) sm.sum[threadIdx.x] = ((sm.grp[0][threadIdx.x] + sm.grp[1][threadIdx.x]) + sm.grp[2][threadIdx.x]) + sm.grp[3][threadIdx.x];
+    __syncthreads();
+  }
+  GCLM_STAMP(5);
+  if (threadIdx.x == 0) {
+    a.tickets[b] = 0u;
+    finish_sums<MODEL, GEN_D>(sm.sum, sm.pc.k1, sm.pc.k2, a.up_scale);  // [g0 g1 X k..] x 1/a_up -> [g0 g1 f k..]
+    sm.last_img = 0;
+    if (a.shared && !pid.is_final) {
+      schur_image<MODEL>(a, pid, b, sm.sum, sm.img);
+      if (a.fused_shared) {  // image-level ticket: the last image's CTA finishes the LM step for the batch
+        __threadfence();
+        if (atomicAdd(&a.ctrl->img_done, 1u) == (unsigned)a.B - 1u) { a.ctrl->img_done = 0u; sm.last_img = 1; }
+      }
+    } else {
+      lm_step_image<MODEL>(a, pid, b, sm.sum, sm.img);
+    }
+  }
+  GCLM_STAMP(6);
+  if (a.shared && a.fused_shared && !pid.is_final) {  // uniform over the grid
+    __syncthreads();
+    if (sm.last_img) shared_tail<MODEL>(a, pid, sm.part, sm.tot);
+  }
+}
+
+// Tiny tiles (small batches: the calibrate() case): every job of a warp is ONE row of one strip.  The whole
+// streaming phase of such a CTA lives in this separate function -- its own accumulators, its own warp reduction
+// into sm.red -- so that the throughput kernel's loop is compiled without it.
+template <int MODEL, bool GEN_D, bool PACK>
+__device__ __noinline__ void stream_single_rows(const PassArgs& a, int b, int tile, CtaSmem<Dims<MODEL>::NACC>& sm) {
+  constexpr int NACC = Dims<MODEL>::NACC;
+  constexpr bool FULL = true;
+  using V = typename std::conditional<PACK, f2, float>::type;
+  const PassConst pc = sm.pc;
+  const RobustConst rc = sm.rc;
+  const FieldMask fm = {true, true, true, true};
+  extern __shared__ __align__(16) unsigned char dyn_smem_s[];
+  const unsigned smem_u32 = (unsigned)__cvta_generic_to_shared(dyn_smem_s);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int W = a.W, H = a.H;
+  const size_t N = (size_t)H * W;
+  const int NS = (W + 127) >> 7;
+  const int yt0 = tile * a.rows_per_tile;
+  const int yt1 = min(H, yt0 + a.rows_per_tile);
+  V acc[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; i++) acc[i] = splat<V>(0.f);
+  {
+      // Tiny tiles (small batches: the calibrate() case): every job is ONE row of one strip, so the row ring has
+      // nothing to prefetch within a job.  Instead the rows of up to RING_STAGES jobs of this warp are fetched
+      // together (one L2 / HBM round trip instead of one per job) and then computed.  Same pixels, same
+      // per-lane accumulation order as the generic loop below (jobs in increasing order) -> same sums.
+      const unsigned plane_stride = blockDim.x * 16u, stage_stride = 5u * plane_stride;
+      const unsigned slot0 = smem_u32 + threadIdx.x * 16u;
+      const int njobs = NS * a.rsub;
+      for (int j0 = warp; j0 < njobs; j0 += nwarps * RING_STAGES) {
+#pragma unroll
+        for (int st = 0; st < RING_STAGES; st++) {
+          const int job = j0 + st * nwarps;
+          const int strip = job % NS, y = yt0 + job / NS, x0 = (strip << 7) + (lane << 2);
+          if (job < njobs && x0 < W && y < yt1) {
+            const size_t off = (size_t)y * W + x0;
+            const unsigned d = slot0 + st * stage_stride;
+            cp_async16(d, a.up + (size_t)b * 2 * N + off); cp_async16(d + plane_stride, a.up + (size_t)b * 2 * N + N + off);
+            cp_async16(d + 2u * plane_stride, a.lat + (size_t)b * N + off);
+            cp_async16(d + 3u * plane_stride, a.uconf + (size_t)b * N + off);
+            cp_async16(d + 4u * plane_stride, a.lconf + (size_t)b * N + off);
+          }
+        }
+        cp_async_commit();
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+        for (int st = 0; st < RING_STAGES; st++) {
+          const int job = j0 + st * nwarps;
+          const int strip = job % NS, y = yt0 + job / NS, x0 = (strip << 7) + (lane << 2);
+          if (job < njobs && x0 < W && y < yt1) {
+            float u[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) u[i] = pixel_u(pc, x0 + i);
+            const unsigned d = slot0 + st * stage_stride;
+            const float4 ox = lds128(d), oy = lds128(d + plane_stride), ol = lds128(d + 2u * plane_stride);
+            const float4 cu = lds128(d + 3u * plane_stride), cl = lds128(d + 4u * plane_stride);
+            row_accumulate<MODEL, GEN_D, FULL, PACK>(pc, fm, make_row_cols<PACK>(pc, u), pixel_v(pc, y), ox, oy, ol, cu, cl,
+                                                     rc, acc, &sm.pc, &sm.rc);
+          }
+        }
+      }
+  }
+#pragma unroll
+  for (int i = 0; i < NACC; i++) {
+    float x = hsum(acc[i]);
+    x += __shfl_xor_sync(0xffffffffu, x, 16);
+    x += __shfl_xor_sync(0xffffffffu, x, 8);
+    x += __shfl_xor_sync(0xffffffffu, x, 4);
+    x += __shfl_xor_sync(0xffffffffu, x, 2);
+    x += __shfl_xor_sync(0xffffffffu, x, 1);
+    if (lane == 0) sm.red[warp][i] = x;
+  }
+}
+
 // One pass of one CTA (a tile of one image): stream, reduce, and -- in the last CTA of the image -- solve.
 // `a` lives in kernel parameter space (never copied); `pid` says which pass this is.
 // IN: how the inputs arrive -- 0 = any subset of the planes (direct 128-bit loads), 1 = all five fp32 planes
@@ -730,58 +960,14 @@ __device__ __forceinline__ void
   const int b = blockIdx.x / a.tiles_per_image;
   const int tile = blockIdx.x - b * a.tiles_per_image;
   GCLM_STAMP(0);
-  __shared__ PassConst s_pc;
-  __shared__ RobustConst s_rc;
-  __shared__ ImgState s_img;
-  __shared__ float s_red[MAX_WARPS][NACC];
-  __shared__ float s_sum[NACC];
-  __shared__ int s_last;
-  __shared__ int s_last_img;
-  __shared__ int s_skip;
-  __shared__ float s_part[MAX_WARPS][SCHUR_NSUM + 3];
-  __shared__ float s_tot[SCHUR_NSUM + 3];
-  if (threadIdx.x == 0) {
-    // everything this CTA (and, if it turns out to be the image's last one, its solver) needs to know about the
-    // image: independent L2 loads, ONE round trip (both parameter buffers are fetched, the slot picks one)
-    int skip = 0;
-    if (a.fused_init && pid.pass == 0 && !pid.is_final) {
-      // first pass of the persistent schedule with the set-up folded in: the state lm_init_kernel would have
-      // written, straight from the caller's initial estimate (Gravity.__init__ normalises, gravity.py:26)
-      for (int i = 0; i < 8; i++) s_img.P[i] = a.cam0[(size_t)b * 8 + i];
-      float g[3] = {a.g0[(size_t)b * 3], a.g0[(size_t)b * 3 + 1], a.g0[(size_t)b * 3 + 2]};
-      normalize3(g);
-      s_img.P[8] = g[0]; s_img.P[9] = g[1]; s_img.P[10] = g[2]; s_img.P[11] = 0.f;
-      s_img.lam = a.lambda0; s_img.prev_cost = 0.f; s_img.slot = 0; s_img.flags = 0u;
-    } else {
-      const int stop = __ldcg(&a.ctrl->stop);
-      const int sl0 = __ldcg(&a.slot[b]);
-      const unsigned fl = __ldcg(&a.flags[b]);
-      const float lam = __ldcg(&a.lam[b]), prev = __ldcg(&a.prev_cost[b]);
-      const float4* P4 = reinterpret_cast<const float4*>(a.P + (size_t)b * 2 * PSTRIDE);
-      float4 q[6];
-#pragma unroll
-      for (int i = 0; i < 6; i++) q[i] = __ldcg(P4 + i);
-      int sl = sl0;
-      if (pid.is_final && stop) sl ^= 1;  // batch stop fired: the tentative update of that pass is dropped
-      const float4 p0 = sl ? q[3] : q[0], p1 = sl ? q[4] : q[1], p2 = sl ? q[5] : q[2];
-      s_img.P[0] = p0.x; s_img.P[1] = p0.y; s_img.P[2] = p0.z; s_img.P[3] = p0.w;
-      s_img.P[4] = p1.x; s_img.P[5] = p1.y; s_img.P[6] = p1.z; s_img.P[7] = p1.w;
-      s_img.P[8] = p2.x; s_img.P[9] = p2.y; s_img.P[10] = p2.z; s_img.P[11] = p2.w;
-      s_img.lam = lam; s_img.prev_cost = prev; s_img.slot = sl0; s_img.flags = fl;
-      skip = !pid.is_final && (stop || (fl & FLAG_FROZEN));
-    }
-    s_skip = skip;
-    if (!skip) {
-      make_pass_const(s_img.P, s_img.P + 8, a.spherical != 0, a.log_focal != 0, pid.is_final != 0 && a.final_rpf != 0, s_pc);
-      s_rc = make_robust_const(a.up_scale, a.lat_scale);
-    }
-  }
+  __shared__ CtaSmem<NACC> sm;
+  if (threadIdx.x == 0) cta_prologue<MODEL>(a, pid, b, sm);
   __syncthreads();
-  if (s_skip) return;  // batch stop latched / image frozen: this pass is a no-op for the CTA
+  if (sm.skip) return;  // batch stop latched / image frozen: this pass is a no-op for the CTA
   GCLM_STAMP(1);
-  const PassConst pc = s_pc;
+  const PassConst pc = sm.pc;
   const FieldMask fm = {a.up != nullptr, a.lat != nullptr, a.uconf != nullptr, a.lconf != nullptr};
-  const RobustConst rc = s_rc;
+  const RobustConst rc = sm.rc;
 
   extern __shared__ __align__(16) unsigned char dyn_smem[];
 #ifdef GCLM_TMA2D
@@ -826,54 +1012,16 @@ __device__ __forceinline__ void
     __syncwarp();
   }
 #endif
-  bool small_done = false;
 #if !defined(GCLM_TMA) && !defined(GCLM_TMA2D)
   if constexpr (IN == 1 && RING_STAGES > 0) {
-    if (RJ == 1) {
-      // Tiny tiles (small batches: the calibrate() case): every job is ONE row of one strip, so the row ring has
-      // nothing to prefetch within a job.  Instead the rows of up to RING_STAGES jobs of this warp are fetched
-      // together (one L2 / HBM round trip instead of one per job) and then computed.  Same pixels, same
-      // per-lane accumulation order as the generic loop below (jobs in increasing order) -> same sums.
-      const unsigned plane_stride = blockDim.x * 16u, stage_stride = 5u * plane_stride;
-      const unsigned slot0 = smem_u32 + threadIdx.x * 16u;
-      const int njobs = NS * a.rsub;
-      for (int j0 = warp; j0 < njobs; j0 += nwarps * RING_STAGES) {
-#pragma unroll
-        for (int st = 0; st < RING_STAGES; st++) {
-          const int job = j0 + st * nwarps;
-          const int strip = job % NS, y = yt0 + job / NS, x0 = (strip << 7) + (lane << 2);
-          if (job < njobs && x0 < W && y < yt1) {
-            const size_t off = (size_t)y * W + x0;
-            const unsigned d = slot0 + st * stage_stride;
-            cp_async16(d, a.up + (size_t)b * 2 * N + off); cp_async16(d + plane_stride, a.up + (size_t)b * 2 * N + N + off);
-            cp_async16(d + 2u * plane_stride, a.lat + (size_t)b * N + off);
-            cp_async16(d + 3u * plane_stride, a.uconf + (size_t)b * N + off);
-            cp_async16(d + 4u * plane_stride, a.lconf + (size_t)b * N + off);
-          }
-        }
-        cp_async_commit();
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
-#pragma unroll
-        for (int st = 0; st < RING_STAGES; st++) {
-          const int job = j0 + st * nwarps;
-          const int strip = job % NS, y = yt0 + job / NS, x0 = (strip << 7) + (lane << 2);
-          if (job < njobs && x0 < W && y < yt1) {
-            float u[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) u[i] = pixel_u(pc, x0 + i);
-            const unsigned d = slot0 + st * stage_stride;
-            const float4 ox = lds128(d), oy = lds128(d + plane_stride), ol = lds128(d + 2u * plane_stride);
-            const float4 cu = lds128(d + 3u * plane_stride), cl = lds128(d + 4u * plane_stride);
-            row_accumulate<MODEL, GEN_D, FULL, PACK>(pc, fm, make_row_cols<PACK>(pc, u), pixel_v(pc, y), ox, oy, ol, cu, cl,
-                                                     rc, acc, &s_pc, &s_rc);
-          }
-        }
-      }
-      small_done = true;
+    if (RJ == 1) {  // tiny tiles: single-row jobs, streamed by their own function (see stream_single_rows)
+      stream_single_rows<MODEL, GEN_D, PACK>(a, b, tile, sm);
+      cta_finish<MODEL, GEN_D, IN>(a, pid, b, tile, sm);
+      return;
     }
   }
 #endif
-  for (int job = warp; !small_done && job < NS * a.rsub; job += nwarps) {
+  for (int job = warp; job < NS * a.rsub; job += nwarps) {
     const int strip = job % NS, sub = job / NS;
     const int x0 = (strip << 7) + (lane << 2);
     const int y0 = yt0 + sub * RJ, y1 = min(yt1, y0 + RJ);
@@ -904,9 +1052,9 @@ __device__ __forceinline__ void
 #endif
       // `ol` already holds target_lat = sin(latitude_field): sin_plane_kernel ran once before pass 0
 #ifdef GCLM_HOIST
-      row_accumulate<MODEL, GEN_D, FULL, PACK>(pc, fm, cols, pixel_v(pc, y), ox, oy, ol, cu, cl, rc, acc, &s_pc, &s_rc);
+      row_accumulate<MODEL, GEN_D, FULL, PACK>(pc, fm, cols, pixel_v(pc, y), ox, oy, ol, cu, cl, rc, acc, &sm.pc, &sm.rc);
 #else
-      row_accumulate<MODEL, GEN_D, FULL, PACK>(pc, fm, make_row_cols<PACK>(pc, u), pixel_v(pc, y), ox, oy, ol, cu, cl, rc, acc, &s_pc, &s_rc);
+      row_accumulate<MODEL, GEN_D, FULL, PACK>(pc, fm, make_row_cols<PACK>(pc, u), pixel_v(pc, y), ox, oy, ol, cu, cl, rc, acc, &sm.pc, &sm.rc);
 #endif
     };
 #ifdef GCLM_TMA2D
@@ -1067,90 +1215,9 @@ __device__ __forceinline__ void
     x += __shfl_xor_sync(0xffffffffu, x, 4);
     x += __shfl_xor_sync(0xffffffffu, x, 2);
     x += __shfl_xor_sync(0xffffffffu, x, 1);
-    if (lane == 0) s_red[warp][i] = x;
+    if (lane == 0) sm.red[warp][i] = x;
   }
-  __syncthreads();
-  const int S = a.tiles_per_image;
-  if (threadIdx.x < NACC) {
-    float s = 0.f;
-    for (int w = 0; w < nwarps; w++) s += s_red[w][threadIdx.x];
-    if (S == 1) s_sum[threadIdx.x] = s;
-    else { a.partials[((size_t)b * S + tile) * NACC + threadIdx.x] = s; __threadfence(); }
-  }
-  __syncthreads();
-  GCLM_STAMP(3);
-  if (S > 1) {
-    if (threadIdx.x == 0) {
-      const unsigned t = atomicAdd(&a.tickets[b], 1u);
-      s_last = (t == (unsigned)S - 1u);
-    }
-    __syncthreads();
-    if (!s_last) return;
-    GCLM_STAMP(4);
-    __threadfence();
-    // deterministic: tile order, independent of arrival order.  All S x NACC partials are fetched by the whole
-    // CTA at once (one L2 round trip) into the idle ring memory when they fit, then added in order.
-    const float* p = a.partials + (size_t)b * S * NACC;
-    float* stage = reinterpret_cast<float*>(dyn_smem);
-    const bool staged = FULL && (size_t)S * NACC * sizeof(float) <= (size_t)RING_STAGES * 5 * blockDim.x * (C16 ? 12 : 16);
-    if (staged) {
-      const int total = S * NACC;
-      for (int i0 = threadIdx.x; i0 < total; i0 += 8 * blockDim.x) {  // 8 loads in flight per thread, then the stores
-        float x[8];
-#pragma unroll
-        for (int k = 0; k < 8; k++) { const int i = i0 + k * blockDim.x; x[k] = i < total ? __ldcg(p + i) : 0.f; }
-#pragma unroll
-        for (int k = 0; k < 8; k++) { const int i = i0 + k * blockDim.x; if (i < total) stage[i] = x[k]; }
-      }
-      __syncthreads();
-    }
-    if (threadIdx.x < NACC) {
-      float s = 0.f;
-      if (staged) {
-        int t = 0;
-        for (; t + 8 <= S; t += 8) {  // loads first (in-order core: a load per add would serialise on LDS latency)
-          float x[8];
-#pragma unroll
-          for (int k = 0; k < 8; k++) x[k] = stage[(t + k) * NACC + threadIdx.x];
-#pragma unroll
-          for (int k = 0; k < 8; k++) s += x[k];
-        }
-        for (; t < S; t++) s += stage[t * NACC + threadIdx.x];
-      } else {
-        int t = 0;
-        for (; t + 8 <= S; t += 8) {  // 8 independent loads in flight, added in tile order
-          float x[8];
-#pragma unroll
-          for (int k = 0; k < 8; k++) x[k] = __ldcg(p + (size_t)(t + k) * NACC + threadIdx.x);
-#pragma unroll
-          for (int k = 0; k < 8; k++) s += x[k];
-        }
-        for (; t < S; t++) s += __ldcg(p + (size_t)t * NACC + threadIdx.x);
-      }
-      s_sum[threadIdx.x] = s;
-    }
-    __syncthreads();
-  }
-  GCLM_STAMP(5);
-  if (threadIdx.x == 0) {
-    a.tickets[b] = 0u;
-    finish_sums<MODEL, GEN_D>(s_sum, pc.k1, pc.k2, a.up_scale);  // [g0 g1 X k..] x 1/a_up -> [g0 g1 f k..]
-    s_last_img = 0;
-    if (a.shared && !pid.is_final) {
-      schur_image<MODEL>(a, pid, b, s_sum, s_img);
-      if (a.fused_shared) {  // image-level ticket: the last image's CTA finishes the LM step for the batch
-        __threadfence();
-        if (atomicAdd(&a.ctrl->img_done, 1u) == (unsigned)a.B - 1u) { a.ctrl->img_done = 0u; s_last_img = 1; }
-      }
-    } else {
-      lm_step_image<MODEL>(a, pid, b, s_sum, s_img);
-    }
-  }
-  GCLM_STAMP(6);
-  if (a.shared && a.fused_shared && !pid.is_final) {  // uniform over the grid
-    __syncthreads();
-    if (s_last_img) shared_tail<MODEL>(a, pid, s_part, s_tot);
-  }
+  cta_finish<MODEL, GEN_D, IN>(a, pid, b, tile, sm);
 }
 
 template <int MODEL, bool GEN_D, int IN, bool PACK>
