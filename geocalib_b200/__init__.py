@@ -10,6 +10,7 @@ The hot path lives in `csrc/` (CUDA + C ABI, built to csrc/libgclm.so); importin
 not need a GPU, running the optimizer does.  There is no CPU fallback.
 """
 
+from .autograd import differentiable_calibrate
 from .camera import BaseCamera, Pinhole, Radial, SimpleDivisional, SimpleRadial, camera_models
 from .extractor import calibrate_batch
 from .gravity import Gravity
@@ -17,6 +18,6 @@ from .lm_optimizer import B200LMOptimizer, LMOptimizer, get_trivial_estimation, 
 
 __all__ = [
     "BaseCamera", "Pinhole", "Radial", "SimpleDivisional", "SimpleRadial", "camera_models",
-    "Gravity", "LMOptimizer", "B200LMOptimizer", "get_trivial_estimation", "install", "calibrate_batch",
+    "Gravity", "LMOptimizer", "B200LMOptimizer", "get_trivial_estimation", "install", "calibrate_batch", "differentiable_calibrate",
 ]
 __version__ = "0.1.0"

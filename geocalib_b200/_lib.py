@@ -86,6 +86,8 @@ SIGNATURES = {
     "gclm_pack_decoder_outputs": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int,
                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gclm_system": (c_int, [c_void_p, POINTER(Problem), POINTER(Options), c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "gclm_adjoint": (c_int, [c_void_p, POINTER(Problem), POINTER(Options), c_void_p, c_void_p, c_void_p,
+                             c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "gclm_solve_shared": (c_int, [c_void_p, POINTER(Problem), POINTER(Options), POINTER(Result), c_void_p, c_void_p]),
     "gclm_comm_unique_id": (c_int, [c_void_p]),
     "gclm_comm_create": (c_int, [c_void_p, c_int, c_int, c_int, POINTER(c_void_p)]),

@@ -1417,6 +1417,109 @@ __global__ void __launch_bounds__(256) pack_decoder_kernel(int B, size_t n4_img,
   }
 }
 
+// ---- differentiable LM: the adjoint pass of the implicit-function backward ----------------------
+// At the LM fixed point G(theta*, x) = J^T W r = 0, so dtheta*/dx = -(dG/dtheta)^-1 dG/dx and for a loss L(theta*)
+//   dL/dx = -d(lambda . G)/dx,   lambda = (dG/dtheta)^-T dL/dtheta          (x = the observed fields / confidences).
+// This kernel evaluates d(lambda . G)/dx per pixel: one streaming pass, no reduction.  G = sum_px [ w_up s e +
+// w_lat l r_lat ] with s, l the Jacobian row scalars (full columns [g0 g1 f k..], LM basis), e = n_perp . o,
+// r_lat = sin(lat_obs) - clamp(l), w = conf / sqrt(max(chi, 1)) (Huber, lm_optimizer.py:61-87):
+//   d/do        = (lambda.s) [ w n_perp + e dw/do ],        dw/do = -w (o - up) / (a^2 chi)  for chi > 1, else 0
+//   d/dlat_obs  = (lambda.l) cos(lat_obs) [ w + r_lat dw/dr ],  dw/dr = -w / r_lat            for chi > 1, else 0
+//   d/dconf     = (lambda.s) e / sqrt(max(chi,1)),   (lambda.l) r_lat / sqrt(max(chi,1))
+// The per-pixel rows are evaluated by the SAME pixel_accumulate the pass kernel uses: with the weights replaced by
+// w_up := 1 (and w_lat := 0, or vice versa) and a single pixel, the "gradient" accumulators it returns are exactly
+// s_i e resp. l_i r_lat, and the diagonal of its "Hessian" s_i^2 -- the adjoint needs only (lambda . s) e etc., so
+// it calls the scalar pixel code twice with unit confidences and reads G.  (Scalar code: one launch per backward.)
+template <int MODEL>
+__global__ void __launch_bounds__(128) lm_adjoint_kernel(int B, int H, int W, const float* __restrict__ up,
+                                                         const float* __restrict__ lat, const float* __restrict__ uconf,
+                                                         const float* __restrict__ lconf, const float* __restrict__ cam,
+                                                         const float* __restrict__ grav, const float* __restrict__ lam,
+                                                         float up_scale, float lat_scale, int spherical, int log_focal,
+                                                         float* __restrict__ g_up, float* __restrict__ g_lat,
+                                                         float* __restrict__ g_uconf, float* __restrict__ g_lconf) {
+  constexpr int NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH, NACC = Dims<MODEL>::NACC;
+  const size_t N = (size_t)H * W;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)B * N) return;
+  const int b = (int)(idx / N);
+  const size_t n = idx - (size_t)b * N;
+  const int y = (int)(n / W), x = (int)(n - (size_t)y * W);
+  float g[3] = {grav[(size_t)b * 3], grav[(size_t)b * 3 + 1], grav[(size_t)b * 3 + 2]};
+  normalize3(g);
+  PassConst pc;
+  make_pass_const(cam + (size_t)b * 8, g, spherical != 0, log_focal != 0, false, pc);
+  const float u = pixel_u(pc, x), v = pixel_v(pc, y);
+  const float ox = up[(size_t)b * 2 * N + n], oy = up[(size_t)b * 2 * N + N + n];
+  const float la = lat[(size_t)b * N + n];
+  const float cu = uconf ? uconf[(size_t)b * N + n] : 1.f, cl = lconf ? lconf[(size_t)b * N + n] : 1.f;
+  const FieldMask fm_up = {true, false, true, false}, fm_lat = {false, true, false, true};
+  // scale 1: the robust form is applied below, here the rows are wanted with unit weights -> make every pixel an
+  // "inlier" of pixel_accumulate by a huge scale (chi << 1, w = conf = 1, finish scale = a_up handled by division)
+  const float BIG = 1e18f;
+  const RobustConst rc1 = make_robust_const(BIG, BIG);
+  const Col<float> col = make_col<float>(pc, u);
+  const float sl = sinf(la);
+  const bool lit = MODEL == SIMPLE_DIVISIONAL && divisional_is_cold(pc, u, v);
+  constexpr bool GEN = true;  // general focal direction code path: columns [g0 g1 f k..] directly (no X basis);
+  const PassConst& pg = pc;   // the log-focal direction d = -uv is selected by dsx = dsy = 1 (make_pass_const)
+  // Forms<MODEL>::HUBER builds return sums scaled by 1/a_up (= 1/BIG): undo
+  const float unscale = Forms<MODEL>::HUBER ? BIG : 1.f;
+  // residuals for the robust terms (recomputed: cheap scalar code)
+  ModelScalars<Dims<MODEL>::K, float> m;
+  const float r2 = u * u + v * v;
+  if (lit) model_scalars<MODEL, float, MODEL == SIMPLE_DIVISIONAL>(pc, r2, m); else model_scalars<MODEL, float>(pc, r2, m);
+  const float p0x = pc.a - pc.c * u, p0y = pc.b - pc.c * v;
+  float px = p0x, py = p0y;
+  if (Dims<MODEL>::K > 0) { const float io = u * p0x + v * p0y; px = m.s * p0x + m.phi * io * u; py = m.s * p0y + m.phi * io * v; }
+  const float irho = 1.f / fmaxf(sqrtf(px * px + py * py), 1e-12f);
+  const float upx = px * irho, upy = py * irho;
+  const float rx = ox - upx, ry = oy - upy;
+  const float e = upx * oy - upy * ox;
+  const float chi_u = (rx * rx + ry * ry) / (up_scale * up_scale);
+  const float isx_u = chi_u > 1.f ? 1.f / sqrtf(chi_u) : 1.f;
+  const float su = Dims<MODEL>::K > 0 ? m.su : 1.f;
+  const float U = su * u, V = su * v, mm = sqrtf(U * U + V * V + 1.f);
+  const float l = (U * pc.a + V * pc.b + pc.c) / mm;
+  const float r_lat = sl - fminf(fmaxf(l, -1.f + 1e-6f), 1.f - 1e-6f);
+  const float chi_l = r_lat * r_lat / (lat_scale * lat_scale);
+  const float isx_l = chi_l > 1.f ? 1.f / sqrtf(chi_l) : 1.f;
+  // (lambda . s) alone: ls_e / e is ill-conditioned near e = 0 -> get it from the derivative form instead:
+  // d(lambda.G_up)/do = w (lambda.s) n_perp + (lambda.s) e dw/do, with n_perp = (-upy, upx).  (lambda.s) is linear
+  // in the rows; pixel_accumulate's G = s e, so run it once more on a probe observation o' = up + n_perp (e' = 1).
+  float ap[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; i++) ap[i] = 0.f;
+  const float qx = upx - upy, qy = upy + upx;  // up + n_perp: e(q) = upx qy - upy qx = 1
+  if (lit) pixel_accumulate<MODEL, GEN, false, float, MODEL == SIMPLE_DIVISIONAL>(pg, fm_up, col, v, qx, qy, sl, 1.f, 1.f, rc1, ap);
+  else pixel_accumulate<MODEL, GEN, false, float>(pg, fm_up, col, v, qx, qy, sl, 1.f, 1.f, rc1, ap);
+  float ls = 0.f;
+#pragma unroll
+  for (int i = 0; i < NF; i++) ls += lam[(size_t)b * NF + i] * ap[NH + i] * unscale;
+  // latitude rows: probe with r_lat' = 1: sin_olat' = clamp(l) + 1
+  float aq[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; i++) aq[i] = 0.f;
+  const float slp = fminf(fmaxf(l, -1.f + 1e-6f), 1.f - 1e-6f) + 1.f;
+  if (lit) pixel_accumulate<MODEL, GEN, false, float, MODEL == SIMPLE_DIVISIONAL>(pg, fm_lat, col, v, ox, oy, slp, 1.f, 1.f, rc1, aq);
+  else pixel_accumulate<MODEL, GEN, false, float>(pg, fm_lat, col, v, ox, oy, slp, 1.f, 1.f, rc1, aq);
+  float ll = 0.f;
+#pragma unroll
+  for (int i = 0; i < NF; i++) ll += lam[(size_t)b * NF + i] * aq[NH + i] * unscale;
+  // ---- assemble ----
+  const float w_u = cu * isx_u, w_l = cl * isx_l;
+  float dwx = 0.f, dwy = 0.f, dwr = 0.f;
+  if (chi_u > 1.f) { const float k = -w_u / (up_scale * up_scale * chi_u); dwx = k * rx; dwy = k * ry; }
+  if (chi_l > 1.f) dwr = -w_l / r_lat;
+  if (g_up) {
+    g_up[(size_t)b * 2 * N + n] = ls * (w_u * (-upy) + e * dwx);
+    g_up[(size_t)b * 2 * N + N + n] = ls * (w_u * upx + e * dwy);
+  }
+  if (g_lat) g_lat[(size_t)b * N + n] = ll * cosf(la) * (w_l + r_lat * dwr);
+  if (g_uconf) g_uconf[(size_t)b * N + n] = ls * e * isx_u;
+  if (g_lconf) g_lconf[(size_t)b * N + n] = ll * r_lat * isx_l;
+}
+
 // counter-based RNG for the synthetic generator (splitmix64 finaliser)
 __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z += 0x9e3779b97f4a7c15ull;
@@ -2268,6 +2371,33 @@ int gclm_system(gclm_handle* h, const gclm_problem* prob, const gclm_options* op
   launch_pass(h, a, rpf_basis ? true : !opt->use_log_focal, full, grid, block, s);
   h->launches += 2;
   order.done();
+  CUDA_TRY(h, cudaGetLastError());
+  return GCLM_OK;
+}
+
+int gclm_adjoint(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt, const float* camera,
+                 const float* gravity, const float* lambda, float* grad_up, float* grad_latitude, float* grad_up_conf,
+                 float* grad_lat_conf, void* cuda_stream) {
+  if (!h || !prob || !opt || !camera || !gravity || !lambda) return GCLM_ERR_INVALID_ARGUMENT;
+  if (prob->batch <= 0 || prob->height <= 0 || prob->width <= 0 || prob->camera_model < 0 || prob->camera_model > 3)
+    return GCLM_ERR_INVALID_ARGUMENT;
+  if (!prob->up_field || !prob->latitude_field) return GCLM_ERR_UNSUPPORTED;  // both fields (the training configuration)
+  DeviceGuard guard(h->device);
+  if (!guard.ok()) return GCLM_ERR_CUDA;
+  cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  const size_t total = (size_t)prob->batch * prob->height * prob->width;
+  const unsigned blocks = (unsigned)((total + 127) / 128);
+#define ADJ(M) lm_adjoint_kernel<M><<<blocks, 128, 0, s>>>(prob->batch, prob->height, prob->width, prob->up_field, prob->latitude_field, \
+    prob->up_confidence, prob->latitude_confidence, camera, gravity, lambda, opt->up_loss_fn_scale, opt->lat_loss_fn_scale, \
+    opt->use_spherical_manifold, opt->use_log_focal, grad_up, grad_latitude, grad_up_conf, grad_lat_conf)
+  switch (prob->camera_model) {
+    case PINHOLE: ADJ(PINHOLE); break;
+    case SIMPLE_RADIAL: ADJ(SIMPLE_RADIAL); break;
+    case RADIAL: ADJ(RADIAL); break;
+    default: ADJ(SIMPLE_DIVISIONAL); break;
+  }
+#undef ADJ
+  h->launches++;
   CUDA_TRY(h, cudaGetLastError());
   return GCLM_OK;
 }

@@ -244,6 +244,32 @@ class Engine:
         return G, Hm, c
 
     # ------------------------------------------------------------------------------------------
+    def adjoint(self, camera_model: str, up_field, latitude_field, up_confidence, latitude_confidence,
+                camera: torch.Tensor, gravity: torch.Tensor, lam: torch.Tensor, *,
+                options: Optional[Options] = None):
+        """gclm_adjoint: d(lambda . G)/d(fields) per pixel at (camera, gravity) -- the streaming pass of the
+        implicit-function backward (geocalib_b200/autograd.py).  Returns 4 tensors shaped like the inputs."""
+        dev = up_field.device
+        B, _, H, W = up_field.shape
+        opt = options if options is not None else _lib.default_options()
+        nf = 3 + NUM_DIST[camera_model]
+        prob = Problem(
+            batch=B, height=H, width=W, camera_model=CAMERA_MODEL_IDS[camera_model],
+            up_field=_dev_ptr(up_field, (B, 2, H, W), "up_field", dev),
+            latitude_field=_dev_ptr(latitude_field, (B, 1, H, W), "latitude_field", dev),
+            up_confidence=_dev_ptr(up_confidence, (B, H, W), "up_confidence", dev),
+            latitude_confidence=_dev_ptr(latitude_confidence, (B, H, W), "latitude_confidence", dev))
+        g_up, g_lat = torch.empty_like(up_field), torch.empty_like(latitude_field)
+        g_uc = torch.empty((B, H, W), device=dev, dtype=torch.float32)
+        g_lc = torch.empty((B, H, W), device=dev, dtype=torch.float32)
+        stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        _lib.check(self.lib.gclm_adjoint(
+            self._h, ctypes.byref(prob), ctypes.byref(opt), _dev_ptr(camera.contiguous(), (B, 8), "camera", dev),
+            _dev_ptr(gravity.contiguous(), (B, 3), "gravity", dev), _dev_ptr(lam.contiguous(), (B, nf), "lambda", dev),
+            g_up.data_ptr(), g_lat.data_ptr(), g_uc.data_ptr(), g_lc.data_ptr(), stream), "gclm_adjoint")
+        return g_up, g_lat, g_uc, g_lc
+
+    # ------------------------------------------------------------------------------------------
     def render_fields(self, camera_model: str, camera: torch.Tensor, gravity: torch.Tensor,
                       height: int, width: int, *, sigma: float = 0.0, conf_lo: float = 1.0,
                       seed: int = 0, with_confidence: bool = True) -> Dict[str, torch.Tensor]:

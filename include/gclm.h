@@ -212,6 +212,20 @@ int gclm_system(gclm_handle* h, const gclm_problem* prob, const gclm_options* op
                 float* gradient, float* hessian, float* costs, void* cuda_stream);
 
 /*
+ * Differentiable LM (reference: the siclib training variant unrolls the LM with autograd,
+ * siclib/models/optimization/lm_optimizer.py:38-57,577-625).  Here the backward pass is the implicit-function
+ * theorem at the converged estimate: G(theta*, x) = J^T W r = 0  =>  dL/dx = -d(lambda . G)/dx with
+ * lambda = (dG/dtheta)^-T dL/dtheta.  gclm_adjoint is that last factor: ONE streaming pass that writes
+ * d(lambda . G)/d(up_field), /d(latitude_field), /d(up_confidence), /d(latitude_confidence) per pixel at the
+ * parameters (camera (B,8), gravity (B,3)) and multipliers lambda (B, 3 + num_dist; full columns [g0 g1 f k..] in
+ * the LM basis selected by opt).  dG/dtheta itself comes from central differences of gclm_system (2 n passes);
+ * geocalib_b200/autograd.py assembles the torch.autograd.Function.  Any output may be NULL.
+ */
+int gclm_adjoint(gclm_handle* h, const gclm_problem* prob, const gclm_options* opt, const float* camera,
+                 const float* gravity, const float* lambda, float* grad_up, float* grad_latitude,
+                 float* grad_up_conf, float* grad_lat_conf, void* cuda_stream);
+
+/*
  * Shared intrinsics: replaces optimize() with shared_intrinsics=True (lm_optimizer.py:350-383,
  * 599-603): one focal / distortion for the whole batch, per-image gravity.  The dense
  * (2B+n_i)^2 arrow system of the reference is solved through its Schur complement.
