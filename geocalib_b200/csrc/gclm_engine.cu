@@ -1430,8 +1430,11 @@ __global__ void __launch_bounds__(256) pack_decoder_kernel(int B, size_t n4_img,
 // w_up := 1 (and w_lat := 0, or vice versa) and a single pixel, the "gradient" accumulators it returns are exactly
 // s_i e resp. l_i r_lat, and the diagonal of its "Hessian" s_i^2 -- the adjoint needs only (lambda . s) e etc., so
 // it calls the scalar pixel code twice with unit confidences and reads G.  (Scalar code: one launch per backward.)
+// Launch: grid (chunks of the image, B), 256 threads; the per-image constants (tangent basis, focal, distortion,
+// lambda) are built once per CTA in shared memory, every thread then walks pixels with a CTA-wide stride (coalesced
+// 4-byte accesses of the 5 input and 5 output planes: 40 B per pixel).
 template <int MODEL>
-__global__ void __launch_bounds__(128) lm_adjoint_kernel(int B, int H, int W, const float* __restrict__ up,
+__global__ void __launch_bounds__(256) lm_adjoint_kernel(int H, int W, const float* __restrict__ up,
                                                          const float* __restrict__ lat, const float* __restrict__ uconf,
                                                          const float* __restrict__ lconf, const float* __restrict__ cam,
                                                          const float* __restrict__ grav, const float* __restrict__ lam,
@@ -1440,84 +1443,101 @@ __global__ void __launch_bounds__(128) lm_adjoint_kernel(int B, int H, int W, co
                                                          float* __restrict__ g_uconf, float* __restrict__ g_lconf) {
   constexpr int NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH, NACC = Dims<MODEL>::NACC;
   const size_t N = (size_t)H * W;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (size_t)B * N) return;
-  const int b = (int)(idx / N);
-  const size_t n = idx - (size_t)b * N;
-  const int y = (int)(n / W), x = (int)(n - (size_t)y * W);
-  float g[3] = {grav[(size_t)b * 3], grav[(size_t)b * 3 + 1], grav[(size_t)b * 3 + 2]};
-  normalize3(g);
-  PassConst pc;
-  make_pass_const(cam + (size_t)b * 8, g, spherical != 0, log_focal != 0, false, pc);
-  const float u = pixel_u(pc, x), v = pixel_v(pc, y);
-  const float ox = up[(size_t)b * 2 * N + n], oy = up[(size_t)b * 2 * N + N + n];
-  const float la = lat[(size_t)b * N + n];
-  const float cu = uconf ? uconf[(size_t)b * N + n] : 1.f, cl = lconf ? lconf[(size_t)b * N + n] : 1.f;
+  const int b = blockIdx.y;
+  __shared__ PassConst pc_s;
+  __shared__ float lam_s[NF];
+  if (threadIdx.x == 0) {
+    float g[3] = {grav[(size_t)b * 3], grav[(size_t)b * 3 + 1], grav[(size_t)b * 3 + 2]};
+    normalize3(g);
+    make_pass_const(cam + (size_t)b * 8, g, spherical != 0, log_focal != 0, false, pc_s);
+  }
+  if (threadIdx.x < NF) lam_s[threadIdx.x] = lam[(size_t)b * NF + threadIdx.x];
+  __syncthreads();
+  const PassConst pc = pc_s;
+  float lm[NF];
+#pragma unroll
+  for (int i = 0; i < NF; i++) lm[i] = lam_s[i];
   const FieldMask fm_up = {true, false, true, false}, fm_lat = {false, true, false, true};
-  // scale 1: the robust form is applied below, here the rows are wanted with unit weights -> make every pixel an
-  // "inlier" of pixel_accumulate by a huge scale (chi << 1, w = conf = 1, finish scale = a_up handled by division)
+  // the rows are wanted with unit weights: a huge robust scale makes every probe an inlier of pixel_accumulate
+  // (w = conf = 1); builds with the scale-folded Huber form return sums scaled by 1/a_up (= 1/BIG): undone below
   const float BIG = 1e18f;
   const RobustConst rc1 = make_robust_const(BIG, BIG);
-  const Col<float> col = make_col<float>(pc, u);
-  const float sl = sinf(la);
-  const bool lit = MODEL == SIMPLE_DIVISIONAL && divisional_is_cold(pc, u, v);
-  constexpr bool GEN = true;  // general focal direction code path: columns [g0 g1 f k..] directly (no X basis);
-  const PassConst& pg = pc;   // the log-focal direction d = -uv is selected by dsx = dsy = 1 (make_pass_const)
-  // Forms<MODEL>::HUBER builds return sums scaled by 1/a_up (= 1/BIG): undo
   const float unscale = Forms<MODEL>::HUBER ? BIG : 1.f;
-  // residuals for the robust terms (recomputed: cheap scalar code)
-  ModelScalars<Dims<MODEL>::K, float> m;
-  const float r2 = u * u + v * v;
-  if (lit) model_scalars<MODEL, float, MODEL == SIMPLE_DIVISIONAL>(pc, r2, m); else model_scalars<MODEL, float>(pc, r2, m);
-  const float p0x = pc.a - pc.c * u, p0y = pc.b - pc.c * v;
-  float px = p0x, py = p0y;
-  if (Dims<MODEL>::K > 0) { const float io = u * p0x + v * p0y; px = m.s * p0x + m.phi * io * u; py = m.s * p0y + m.phi * io * v; }
-  const float irho = 1.f / fmaxf(sqrtf(px * px + py * py), 1e-12f);
-  const float upx = px * irho, upy = py * irho;
-  const float rx = ox - upx, ry = oy - upy;
-  const float e = upx * oy - upy * ox;
-  const float chi_u = (rx * rx + ry * ry) / (up_scale * up_scale);
-  const float isx_u = chi_u > 1.f ? 1.f / sqrtf(chi_u) : 1.f;
-  const float su = Dims<MODEL>::K > 0 ? m.su : 1.f;
-  const float U = su * u, V = su * v, mm = sqrtf(U * U + V * V + 1.f);
-  const float l = (U * pc.a + V * pc.b + pc.c) / mm;
-  const float r_lat = sl - fminf(fmaxf(l, -1.f + 1e-6f), 1.f - 1e-6f);
-  const float chi_l = r_lat * r_lat / (lat_scale * lat_scale);
-  const float isx_l = chi_l > 1.f ? 1.f / sqrtf(chi_l) : 1.f;
-  // (lambda . s) alone: ls_e / e is ill-conditioned near e = 0 -> get it from the derivative form instead:
-  // d(lambda.G_up)/do = w (lambda.s) n_perp + (lambda.s) e dw/do, with n_perp = (-upy, upx).  (lambda.s) is linear
-  // in the rows; pixel_accumulate's G = s e, so run it once more on a probe observation o' = up + n_perp (e' = 1).
-  float ap[NACC];
+  const float iu2 = 1.f / (up_scale * up_scale), il2 = 1.f / (lat_scale * lat_scale);
+  up += (size_t)b * 2 * N; lat += (size_t)b * N;
+  if (uconf) uconf += (size_t)b * N;
+  if (lconf) lconf += (size_t)b * N;
+  if (g_up) g_up += (size_t)b * 2 * N;
+  if (g_lat) g_lat += (size_t)b * N;
+  if (g_uconf) g_uconf += (size_t)b * N;
+  if (g_lconf) g_lconf += (size_t)b * N;
+  for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (size_t)gridDim.x * blockDim.x) {
+    const int y = (int)(n / W), x = (int)(n - (size_t)y * W);
+    const float u = pixel_u(pc, x), v = pixel_v(pc, y);
+    const float ox = __ldg(up + n), oy = __ldg(up + N + n);
+    const float la = __ldg(lat + n);
+    const float cu = uconf ? __ldg(uconf + n) : 1.f, cl = lconf ? __ldg(lconf + n) : 1.f;
+    const Col<float> col = make_col<float>(pc, u);
+    float sl, cla;
+    sincosf(la, &sl, &cla);
+    const bool lit = MODEL == SIMPLE_DIVISIONAL && divisional_is_cold(pc, u, v);
+    // predicted up vector / latitude and the residuals of the robust terms (scalar code, general focal direction:
+    // columns [g0 g1 f k..] directly; the log-focal direction d = -uv is selected by dsx = dsy = 1 in make_pass_const)
+    ModelScalars<Dims<MODEL>::K, float> m;
+    const float r2 = u * u + v * v;
+    if (lit) model_scalars<MODEL, float, MODEL == SIMPLE_DIVISIONAL>(pc, r2, m); else model_scalars<MODEL, float>(pc, r2, m);
+    const float p0x = pc.a - pc.c * u, p0y = pc.b - pc.c * v;
+    float px = p0x, py = p0y;
+    if (Dims<MODEL>::K > 0) { const float io = u * p0x + v * p0y; px = m.s * p0x + m.phi * io * u; py = m.s * p0y + m.phi * io * v; }
+    const float irho = rsqrtf(fmaxf(px * px + py * py, 1e-24f));
+    const float upx = px * irho, upy = py * irho;
+    const float rx = ox - upx, ry = oy - upy;
+    const float e = upx * oy - upy * ox;
+    const float c2u = rx * rx + ry * ry;
+    const float chi_u = c2u * iu2;
+    const float isx_u = chi_u > 1.f ? rsqrtf(chi_u) : 1.f;
+    const float su = Dims<MODEL>::K > 0 ? m.su : 1.f;
+    const float U = su * u, V = su * v;
+    const float l = (U * pc.a + V * pc.b + pc.c) * rsqrtf(U * U + V * V + 1.f);
+    const float lc = fminf(fmaxf(l, -1.f + 1e-6f), 1.f - 1e-6f);
+    const float r_lat = sl - lc;
+    const float chi_l = r_lat * r_lat * il2;
+    const float isx_l = chi_l > 1.f ? rsqrtf(chi_l) : 1.f;
+    // (lambda . s): d(lambda.G_up)/do = w (lambda.s) n_perp + (lambda.s) e dw/do with n_perp = (-upy, upx).  The rows
+    // enter pixel_accumulate's G linearly (G = s e), so probe it with o' = up + n_perp (e' = 1) ...
+    float ap[NACC];
 #pragma unroll
-  for (int i = 0; i < NACC; i++) ap[i] = 0.f;
-  const float qx = upx - upy, qy = upy + upx;  // up + n_perp: e(q) = upx qy - upy qx = 1
-  if (lit) pixel_accumulate<MODEL, GEN, false, float, MODEL == SIMPLE_DIVISIONAL>(pg, fm_up, col, v, qx, qy, sl, 1.f, 1.f, rc1, ap);
-  else pixel_accumulate<MODEL, GEN, false, float>(pg, fm_up, col, v, qx, qy, sl, 1.f, 1.f, rc1, ap);
-  float ls = 0.f;
+    for (int i = 0; i < NACC; i++) ap[i] = 0.f;
+    const float qx = upx - upy, qy = upy + upx;
+    if (lit) pixel_accumulate<MODEL, true, false, float, MODEL == SIMPLE_DIVISIONAL>(pc, fm_up, col, v, qx, qy, sl, 1.f, 1.f, rc1, ap);
+    else pixel_accumulate<MODEL, true, false, float>(pc, fm_up, col, v, qx, qy, sl, 1.f, 1.f, rc1, ap);
+    float ls = 0.f;
 #pragma unroll
-  for (int i = 0; i < NF; i++) ls += lam[(size_t)b * NF + i] * ap[NH + i] * unscale;
-  // latitude rows: probe with r_lat' = 1: sin_olat' = clamp(l) + 1
-  float aq[NACC];
+    for (int i = 0; i < NF; i++) ls = fmaf(lm[i], ap[NH + i], ls);
+    ls *= unscale;
+    // ... and the latitude rows with r_lat' = 1: sin_olat' = clamp(l) + 1
+    float aq[NACC];
 #pragma unroll
-  for (int i = 0; i < NACC; i++) aq[i] = 0.f;
-  const float slp = fminf(fmaxf(l, -1.f + 1e-6f), 1.f - 1e-6f) + 1.f;
-  if (lit) pixel_accumulate<MODEL, GEN, false, float, MODEL == SIMPLE_DIVISIONAL>(pg, fm_lat, col, v, ox, oy, slp, 1.f, 1.f, rc1, aq);
-  else pixel_accumulate<MODEL, GEN, false, float>(pg, fm_lat, col, v, ox, oy, slp, 1.f, 1.f, rc1, aq);
-  float ll = 0.f;
+    for (int i = 0; i < NACC; i++) aq[i] = 0.f;
+    if (lit) pixel_accumulate<MODEL, true, false, float, MODEL == SIMPLE_DIVISIONAL>(pc, fm_lat, col, v, ox, oy, lc + 1.f, 1.f, 1.f, rc1, aq);
+    else pixel_accumulate<MODEL, true, false, float>(pc, fm_lat, col, v, ox, oy, lc + 1.f, 1.f, 1.f, rc1, aq);
+    float ll = 0.f;
 #pragma unroll
-  for (int i = 0; i < NF; i++) ll += lam[(size_t)b * NF + i] * aq[NH + i] * unscale;
-  // ---- assemble ----
-  const float w_u = cu * isx_u, w_l = cl * isx_l;
-  float dwx = 0.f, dwy = 0.f, dwr = 0.f;
-  if (chi_u > 1.f) { const float k = -w_u / (up_scale * up_scale * chi_u); dwx = k * rx; dwy = k * ry; }
-  if (chi_l > 1.f) dwr = -w_l / r_lat;
-  if (g_up) {
-    g_up[(size_t)b * 2 * N + n] = ls * (w_u * (-upy) + e * dwx);
-    g_up[(size_t)b * 2 * N + N + n] = ls * (w_u * upx + e * dwy);
+    for (int i = 0; i < NF; i++) ll = fmaf(lm[i], aq[NH + i], ll);
+    ll *= unscale;
+    // ---- assemble ----
+    const float w_u = cu * isx_u, w_l = cl * isx_l;
+    float dwx = 0.f, dwy = 0.f, lat_term = w_l;  // w + r dw/dr = 0 for latitude outliers (|r| enters G as sign(r))
+    if (chi_u > 1.f) { const float k = -__fdividef(w_u, c2u); dwx = k * rx; dwy = k * ry; }
+    if (chi_l > 1.f) lat_term = 0.f;
+    if (g_up) {
+      g_up[n] = ls * (w_u * (-upy) + e * dwx);
+      g_up[N + n] = ls * (w_u * upx + e * dwy);
+    }
+    if (g_lat) g_lat[n] = ll * cla * lat_term;
+    if (g_uconf) g_uconf[n] = ls * e * isx_u;
+    if (g_lconf) g_lconf[n] = ll * r_lat * isx_l;
   }
-  if (g_lat) g_lat[(size_t)b * N + n] = ll * cosf(la) * (w_l + r_lat * dwr);
-  if (g_uconf) g_uconf[(size_t)b * N + n] = ls * e * isx_u;
-  if (g_lconf) g_lconf[(size_t)b * N + n] = ll * r_lat * isx_l;
 }
 
 // counter-based RNG for the synthetic generator (splitmix64 finaliser)
@@ -2385,9 +2405,12 @@ int gclm_adjoint(gclm_handle* h, const gclm_problem* prob, const gclm_options* o
   DeviceGuard guard(h->device);
   if (!guard.ok()) return GCLM_ERR_CUDA;
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-  const size_t total = (size_t)prob->batch * prob->height * prob->width;
-  const unsigned blocks = (unsigned)((total + 127) / 128);
-#define ADJ(M) lm_adjoint_kernel<M><<<blocks, 128, 0, s>>>(prob->batch, prob->height, prob->width, prob->up_field, prob->latitude_field, \
+  // >= 8 pixels per thread (amortises the per-CTA constants), <= 65535 images per launch (grid.y)
+  const size_t px = (size_t)prob->height * prob->width;
+  const unsigned chunks = (unsigned)std::max<size_t>(1, std::min<size_t>((px + 2047) / 2048, 1u << 16));
+  if (prob->batch > 65535) return GCLM_ERR_UNSUPPORTED;
+  const dim3 grid(chunks, (unsigned)prob->batch);
+#define ADJ(M) lm_adjoint_kernel<M><<<grid, 256, 0, s>>>(prob->height, prob->width, prob->up_field, prob->latitude_field, \
     prob->up_confidence, prob->latitude_confidence, camera, gravity, lambda, opt->up_loss_fn_scale, opt->lat_loss_fn_scale, \
     opt->use_spherical_manifold, opt->use_log_focal, grad_up, grad_latitude, grad_up_conf, grad_lat_conf)
   switch (prob->camera_model) {
