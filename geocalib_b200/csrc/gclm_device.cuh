@@ -661,6 +661,78 @@ GCLM_HD __noinline__ void pixel_scalar(const PassConst& pc, const FieldMask fm, 
 GCLM_HD __forceinline__ float pixel_u(const PassConst& pc, int x) { return ((float)x - pc.cx) * pc.inv_fx; }
 GCLM_HD __forceinline__ float pixel_v(const PassConst& pc, int y) { return ((float)y - pc.cy) * pc.inv_fy; }
 
+// ---- differentiable LM: one pixel of the adjoint pass (gclm_engine.cu: lm_adjoint_kernel) ----
+// d(lambda . G)/dx for the five input values of one pixel, G = sum_px [w_up s e + w_lat l r_lat] the LM gradient
+// J^T W r with s, l the Jacobian row scalars (full columns [g0 g1 f k..]), e = n_perp . o, r_lat = sin(lat_obs) -
+// clamp(l), w = conf / sqrt(max(chi, 1)) (Huber, lm_optimizer.py:61-87):
+//   d/do        = (lambda.s) [ w n_perp + e dw/do ],       dw/do = -w (o - up)/|o - up|^2 for chi > 1, else 0
+//   d/dlat_obs  = (lambda.l) cos(lat_obs) w for chi <= 1, 0 for chi > 1 (there w r_lat = conf a sign(r_lat))
+//   d/dconf     = (lambda.s) e / sqrt(max(chi,1)),   (lambda.l) r_lat / sqrt(max(chi,1))
+// The rows come from the SAME pixel_accumulate the pass kernel uses: they enter its G linearly (G_i = w s_i e), so it
+// is probed with unit confidences, a robust scale that makes every probe an inlier (rc_probe = make_robust_const(BIG,
+// BIG), unscale = BIG for the scale-folded Huber builds, else 1) and observations chosen such that e' = 1 (o' = up +
+// n_perp) resp. r_lat' = 1.  out = [d/dox, d/doy, d/dlat, d/dconf_up, d/dconf_lat].  Host-compilable
+// (tests/host_math): checked per pixel against fp64 finite differences of the oracle system without a GPU.
+template <int MODEL>
+GCLM_HD inline void adjoint_pixel(const PassConst& pc, const float* lm, const RobustConst& rc_probe, float unscale,
+                                  float inv_up_s2, float inv_lat_s2, float u, float v, float ox, float oy, float la,
+                                  float cu, float cl, float out[5]) {
+  constexpr int K = Dims<MODEL>::K, NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH, NACC = Dims<MODEL>::NACC;
+  const FieldMask fm_up = {true, false, true, false}, fm_lat = {false, true, false, true};
+  const Col<float> col = make_col<float>(pc, u);
+  const float sl = sinf(la), cla = cosf(la);
+  const bool lit = MODEL == SIMPLE_DIVISIONAL && divisional_is_cold(pc, u, v);
+  // predicted up vector / latitude and the residuals of the robust terms (general focal direction code: columns
+  // [g0 g1 f k..] directly; the log-focal direction d = -uv is selected by dsx = dsy = 1 in make_pass_const)
+  ModelScalars<K, float> m;
+  const float r2 = u * u + v * v;
+  if (lit) model_scalars<MODEL, float, MODEL == SIMPLE_DIVISIONAL>(pc, r2, m); else model_scalars<MODEL, float>(pc, r2, m);
+  const float p0x = pc.a - pc.c * u, p0y = pc.b - pc.c * v;
+  float px = p0x, py = p0y;
+  if (K > 0) { const float io = u * p0x + v * p0y; px = m.s * p0x + m.phi * io * u; py = m.s * p0y + m.phi * io * v; }
+  const float irho = fast_rsqrt(fmaxf(px * px + py * py, 1e-24f));
+  const float upx = px * irho, upy = py * irho;
+  const float rx = ox - upx, ry = oy - upy;
+  const float e = upx * oy - upy * ox;
+  const float c2u = rx * rx + ry * ry;
+  const float chi_u = c2u * inv_up_s2;
+  const float isx_u = chi_u > 1.f ? fast_rsqrt(chi_u) : 1.f;
+  const float su = K > 0 ? m.su : 1.f;
+  const float U = su * u, V = su * v;
+  const float l = (U * pc.a + V * pc.b + pc.c) * fast_rsqrt(U * U + V * V + 1.f);
+  const float lc = fminf(fmaxf(l, -1.f + 1e-6f), 1.f - 1e-6f);
+  const float r_lat = sl - lc;
+  const float chi_l = r_lat * r_lat * inv_lat_s2;
+  const float isx_l = chi_l > 1.f ? fast_rsqrt(chi_l) : 1.f;
+  float ap[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; i++) ap[i] = 0.f;
+  const float qx = upx - upy, qy = upy + upx;  // up + n_perp: e(q) = upx qy - upy qx = 1
+  if (lit) pixel_accumulate<MODEL, true, false, float, MODEL == SIMPLE_DIVISIONAL>(pc, fm_up, col, v, qx, qy, sl, 1.f, 1.f, rc_probe, ap);
+  else pixel_accumulate<MODEL, true, false, float>(pc, fm_up, col, v, qx, qy, sl, 1.f, 1.f, rc_probe, ap);
+  float ls = 0.f;
+#pragma unroll
+  for (int i = 0; i < NF; i++) ls = fmaf(lm[i], ap[NH + i], ls);
+  ls *= unscale;
+  float aq[NACC];
+#pragma unroll
+  for (int i = 0; i < NACC; i++) aq[i] = 0.f;
+  if (lit) pixel_accumulate<MODEL, true, false, float, MODEL == SIMPLE_DIVISIONAL>(pc, fm_lat, col, v, ox, oy, lc + 1.f, 1.f, 1.f, rc_probe, aq);
+  else pixel_accumulate<MODEL, true, false, float>(pc, fm_lat, col, v, ox, oy, lc + 1.f, 1.f, 1.f, rc_probe, aq);
+  float ll = 0.f;
+#pragma unroll
+  for (int i = 0; i < NF; i++) ll = fmaf(lm[i], aq[NH + i], ll);
+  ll *= unscale;
+  const float w_u = cu * isx_u, w_l = cl * isx_l;
+  float dwx = 0.f, dwy = 0.f;
+  if (chi_u > 1.f) { const float k = -(w_u * fast_rcp(c2u)); dwx = k * rx; dwy = k * ry; }
+  out[0] = ls * (w_u * (-upy) + e * dwx);
+  out[1] = ls * (w_u * upx + e * dwy);
+  out[2] = chi_l > 1.f ? 0.f : ll * cla * w_l;
+  out[3] = ls * e * isx_u;
+  out[4] = ll * r_lat * isx_l;
+}
+
 // Four consecutive pixels of one image row (one float4 of every plane; `ol` = sin(latitude)) into the
 // accumulators: the body of lm_pass_kernel's streaming loop, also run on the host by tests/host_math.
 // The column terms of the four consecutive pixels a lane owns (two pairs when packed).

@@ -1420,16 +1420,7 @@ __global__ void __launch_bounds__(256) pack_decoder_kernel(int B, size_t n4_img,
 // ---- differentiable LM: the adjoint pass of the implicit-function backward ----------------------
 // At the LM fixed point G(theta*, x) = J^T W r = 0, so dtheta*/dx = -(dG/dtheta)^-1 dG/dx and for a loss L(theta*)
 //   dL/dx = -d(lambda . G)/dx,   lambda = (dG/dtheta)^-T dL/dtheta          (x = the observed fields / confidences).
-// This kernel evaluates d(lambda . G)/dx per pixel: one streaming pass, no reduction.  G = sum_px [ w_up s e +
-// w_lat l r_lat ] with s, l the Jacobian row scalars (full columns [g0 g1 f k..], LM basis), e = n_perp . o,
-// r_lat = sin(lat_obs) - clamp(l), w = conf / sqrt(max(chi, 1)) (Huber, lm_optimizer.py:61-87):
-//   d/do        = (lambda.s) [ w n_perp + e dw/do ],        dw/do = -w (o - up) / (a^2 chi)  for chi > 1, else 0
-//   d/dlat_obs  = (lambda.l) cos(lat_obs) [ w + r_lat dw/dr ],  dw/dr = -w / r_lat            for chi > 1, else 0
-//   d/dconf     = (lambda.s) e / sqrt(max(chi,1)),   (lambda.l) r_lat / sqrt(max(chi,1))
-// The per-pixel rows are evaluated by the SAME pixel_accumulate the pass kernel uses: with the weights replaced by
-// w_up := 1 (and w_lat := 0, or vice versa) and a single pixel, the "gradient" accumulators it returns are exactly
-// s_i e resp. l_i r_lat, and the diagonal of its "Hessian" s_i^2 -- the adjoint needs only (lambda . s) e etc., so
-// it calls the scalar pixel code twice with unit confidences and reads G.  (Scalar code: one launch per backward.)
+// This kernel evaluates d(lambda . G)/dx per pixel (gclm_device.cuh: adjoint_pixel): one streaming pass, no reduction.
 // Launch: grid (chunks of the image, B), 256 threads; the per-image constants (tangent basis, focal, distortion,
 // lambda) are built once per CTA in shared memory, every thread then walks pixels with a CTA-wide stride (coalesced
 // 4-byte accesses of the 5 input and 5 output planes: 40 B per pixel).
@@ -1441,7 +1432,7 @@ __global__ void __launch_bounds__(256) lm_adjoint_kernel(int H, int W, const flo
                                                          float up_scale, float lat_scale, int spherical, int log_focal,
                                                          float* __restrict__ g_up, float* __restrict__ g_lat,
                                                          float* __restrict__ g_uconf, float* __restrict__ g_lconf) {
-  constexpr int NF = Dims<MODEL>::NF, NH = Dims<MODEL>::NH, NACC = Dims<MODEL>::NACC;
+  constexpr int NF = Dims<MODEL>::NF;
   const size_t N = (size_t)H * W;
   const int b = blockIdx.y;
   __shared__ PassConst pc_s;
@@ -1457,11 +1448,8 @@ __global__ void __launch_bounds__(256) lm_adjoint_kernel(int H, int W, const flo
   float lm[NF];
 #pragma unroll
   for (int i = 0; i < NF; i++) lm[i] = lam_s[i];
-  const FieldMask fm_up = {true, false, true, false}, fm_lat = {false, true, false, true};
-  // the rows are wanted with unit weights: a huge robust scale makes every probe an inlier of pixel_accumulate
-  // (w = conf = 1); builds with the scale-folded Huber form return sums scaled by 1/a_up (= 1/BIG): undone below
   const float BIG = 1e18f;
-  const RobustConst rc1 = make_robust_const(BIG, BIG);
+  const RobustConst rc_probe = make_robust_const(BIG, BIG);
   const float unscale = Forms<MODEL>::HUBER ? BIG : 1.f;
   const float iu2 = 1.f / (up_scale * up_scale), il2 = 1.f / (lat_scale * lat_scale);
   up += (size_t)b * 2 * N; lat += (size_t)b * N;
@@ -1473,70 +1461,13 @@ __global__ void __launch_bounds__(256) lm_adjoint_kernel(int H, int W, const flo
   if (g_lconf) g_lconf += (size_t)b * N;
   for (size_t n = (size_t)blockIdx.x * blockDim.x + threadIdx.x; n < N; n += (size_t)gridDim.x * blockDim.x) {
     const int y = (int)(n / W), x = (int)(n - (size_t)y * W);
-    const float u = pixel_u(pc, x), v = pixel_v(pc, y);
-    const float ox = __ldg(up + n), oy = __ldg(up + N + n);
-    const float la = __ldg(lat + n);
-    const float cu = uconf ? __ldg(uconf + n) : 1.f, cl = lconf ? __ldg(lconf + n) : 1.f;
-    const Col<float> col = make_col<float>(pc, u);
-    float sl, cla;
-    sincosf(la, &sl, &cla);
-    const bool lit = MODEL == SIMPLE_DIVISIONAL && divisional_is_cold(pc, u, v);
-    // predicted up vector / latitude and the residuals of the robust terms (scalar code, general focal direction:
-    // columns [g0 g1 f k..] directly; the log-focal direction d = -uv is selected by dsx = dsy = 1 in make_pass_const)
-    ModelScalars<Dims<MODEL>::K, float> m;
-    const float r2 = u * u + v * v;
-    if (lit) model_scalars<MODEL, float, MODEL == SIMPLE_DIVISIONAL>(pc, r2, m); else model_scalars<MODEL, float>(pc, r2, m);
-    const float p0x = pc.a - pc.c * u, p0y = pc.b - pc.c * v;
-    float px = p0x, py = p0y;
-    if (Dims<MODEL>::K > 0) { const float io = u * p0x + v * p0y; px = m.s * p0x + m.phi * io * u; py = m.s * p0y + m.phi * io * v; }
-    const float irho = rsqrtf(fmaxf(px * px + py * py, 1e-24f));
-    const float upx = px * irho, upy = py * irho;
-    const float rx = ox - upx, ry = oy - upy;
-    const float e = upx * oy - upy * ox;
-    const float c2u = rx * rx + ry * ry;
-    const float chi_u = c2u * iu2;
-    const float isx_u = chi_u > 1.f ? rsqrtf(chi_u) : 1.f;
-    const float su = Dims<MODEL>::K > 0 ? m.su : 1.f;
-    const float U = su * u, V = su * v;
-    const float l = (U * pc.a + V * pc.b + pc.c) * rsqrtf(U * U + V * V + 1.f);
-    const float lc = fminf(fmaxf(l, -1.f + 1e-6f), 1.f - 1e-6f);
-    const float r_lat = sl - lc;
-    const float chi_l = r_lat * r_lat * il2;
-    const float isx_l = chi_l > 1.f ? rsqrtf(chi_l) : 1.f;
-    // (lambda . s): d(lambda.G_up)/do = w (lambda.s) n_perp + (lambda.s) e dw/do with n_perp = (-upy, upx).  The rows
-    // enter pixel_accumulate's G linearly (G = s e), so probe it with o' = up + n_perp (e' = 1) ...
-    float ap[NACC];
-#pragma unroll
-    for (int i = 0; i < NACC; i++) ap[i] = 0.f;
-    const float qx = upx - upy, qy = upy + upx;
-    if (lit) pixel_accumulate<MODEL, true, false, float, MODEL == SIMPLE_DIVISIONAL>(pc, fm_up, col, v, qx, qy, sl, 1.f, 1.f, rc1, ap);
-    else pixel_accumulate<MODEL, true, false, float>(pc, fm_up, col, v, qx, qy, sl, 1.f, 1.f, rc1, ap);
-    float ls = 0.f;
-#pragma unroll
-    for (int i = 0; i < NF; i++) ls = fmaf(lm[i], ap[NH + i], ls);
-    ls *= unscale;
-    // ... and the latitude rows with r_lat' = 1: sin_olat' = clamp(l) + 1
-    float aq[NACC];
-#pragma unroll
-    for (int i = 0; i < NACC; i++) aq[i] = 0.f;
-    if (lit) pixel_accumulate<MODEL, true, false, float, MODEL == SIMPLE_DIVISIONAL>(pc, fm_lat, col, v, ox, oy, lc + 1.f, 1.f, 1.f, rc1, aq);
-    else pixel_accumulate<MODEL, true, false, float>(pc, fm_lat, col, v, ox, oy, lc + 1.f, 1.f, 1.f, rc1, aq);
-    float ll = 0.f;
-#pragma unroll
-    for (int i = 0; i < NF; i++) ll = fmaf(lm[i], aq[NH + i], ll);
-    ll *= unscale;
-    // ---- assemble ----
-    const float w_u = cu * isx_u, w_l = cl * isx_l;
-    float dwx = 0.f, dwy = 0.f, lat_term = w_l;  // w + r dw/dr = 0 for latitude outliers (|r| enters G as sign(r))
-    if (chi_u > 1.f) { const float k = -__fdividef(w_u, c2u); dwx = k * rx; dwy = k * ry; }
-    if (chi_l > 1.f) lat_term = 0.f;
-    if (g_up) {
-      g_up[n] = ls * (w_u * (-upy) + e * dwx);
-      g_up[N + n] = ls * (w_u * upx + e * dwy);
-    }
-    if (g_lat) g_lat[n] = ll * cla * lat_term;
-    if (g_uconf) g_uconf[n] = ls * e * isx_u;
-    if (g_lconf) g_lconf[n] = ll * r_lat * isx_l;
+    float d[5];
+    adjoint_pixel<MODEL>(pc, lm, rc_probe, unscale, iu2, il2, pixel_u(pc, x), pixel_v(pc, y), __ldg(up + n), __ldg(up + N + n),
+                         __ldg(lat + n), uconf ? __ldg(uconf + n) : 1.f, lconf ? __ldg(lconf + n) : 1.f, d);
+    if (g_up) { g_up[n] = d[0]; g_up[N + n] = d[1]; }
+    if (g_lat) g_lat[n] = d[2];
+    if (g_uconf) g_uconf[n] = d[3];
+    if (g_lconf) g_lconf[n] = d[4];
   }
 }
 
@@ -2405,6 +2336,7 @@ int gclm_adjoint(gclm_handle* h, const gclm_problem* prob, const gclm_options* o
   DeviceGuard guard(h->device);
   if (!guard.ok()) return GCLM_ERR_CUDA;
   cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+  std::lock_guard<std::mutex> lk(h->mu);
   // >= 8 pixels per thread (amortises the per-CTA constants), <= 65535 images per launch (grid.y)
   const size_t px = (size_t)prob->height * prob->width;
   const unsigned chunks = (unsigned)std::max<size_t>(1, std::min<size_t>((px + 2047) / 2048, 1u << 16));

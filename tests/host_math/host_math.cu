@@ -73,3 +73,40 @@ extern "C" int gclm_host_math_system(int model, int H, int W, const float* up, c
     default: dispatch<SIMPLE_DIVISIONAL>(gen_d, pack, pc, f, up_scale, lat_scale, out); return Dims<SIMPLE_DIVISIONAL>::NACC;
   }
 }
+
+// The adjoint pass of the differentiable LM (gclm_device.cuh: adjoint_pixel, the body of lm_adjoint_kernel) on the
+// host: out = (5, H, W) planes [d/dox, d/doy, d/dlat, d/dconf_up, d/dconf_lat] of lambda . G.
+namespace {
+template <int MODEL>
+void run_adjoint(const PassConst& pc, const Fields& f, const float* lam, float up_scale, float lat_scale, float* out) {
+  const float BIG = 1e18f;
+  const RobustConst rc_probe = make_robust_const(BIG, BIG);
+  const float unscale = Forms<MODEL>::HUBER ? BIG : 1.f;
+  const float iu2 = 1.f / (up_scale * up_scale), il2 = 1.f / (lat_scale * lat_scale);
+  const size_t N = (size_t)f.H * f.W;
+  for (int y = 0; y < f.H; y++)
+    for (int x = 0; x < f.W; x++) {
+      const size_t n = (size_t)y * f.W + x;
+      float d[5];
+      adjoint_pixel<MODEL>(pc, lam, rc_probe, unscale, iu2, il2, pixel_u(pc, x), pixel_v(pc, y), f.up[n], f.up[N + n], f.lat[n],
+                           f.uconf[n], f.lconf[n], d);
+      for (int k = 0; k < 5; k++) out[(size_t)k * N + n] = d[k];
+    }
+}
+}  // namespace
+
+extern "C" int gclm_host_math_adjoint(int model, int H, int W, const float* up, const float* lat, const float* uconf,
+                                      const float* lconf, const float* cam, const float* grav, const float* lam,
+                                      float up_scale, float lat_scale, float* out) {
+  if (H <= 0 || W <= 0 || model < 0 || model > 3) return -1;
+  PassConst pc;
+  make_pass_const(cam, grav, true, true, false, pc);  // spherical manifold + log focal: the training configuration
+  const Fields f = {H, W, up, lat, uconf, lconf};
+  switch (model) {
+    case PINHOLE: run_adjoint<PINHOLE>(pc, f, lam, up_scale, lat_scale, out); break;
+    case SIMPLE_RADIAL: run_adjoint<SIMPLE_RADIAL>(pc, f, lam, up_scale, lat_scale, out); break;
+    case RADIAL: run_adjoint<RADIAL>(pc, f, lam, up_scale, lat_scale, out); break;
+    default: run_adjoint<SIMPLE_DIVISIONAL>(pc, f, lam, up_scale, lat_scale, out); break;
+  }
+  return 0;
+}

@@ -35,6 +35,8 @@ def hostmath():
     fp, dp = ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_double)
     L.gclm_host_math_system.restype = ctypes.c_int
     L.gclm_host_math_system.argtypes = [ctypes.c_int] * 3 + [fp] * 6 + [ctypes.c_int] * 5 + [ctypes.c_float] * 2 + [dp]
+    L.gclm_host_math_adjoint.restype = ctypes.c_int
+    L.gclm_host_math_adjoint.argtypes = [ctypes.c_int] * 3 + [fp] * 7 + [ctypes.c_float] * 2 + [fp]
     return L
 
 
@@ -135,3 +137,42 @@ def test_divisional_clamped_root_pixels(hostmath, pack):
                       rpf=False, pack=pack)
     ref = oracle.system("simple_divisional", cam, grav, up, lat[None], uconf, lconf, dtype=np.float64)
     assert_system_close(got, ref, tol=2e-4)  # Jacobians blow up next to the clamp (condition number ~1e10)
+
+
+@pytest.mark.parametrize("scale", [1e-2, 0.2], ids=["default_scale_mostly_outliers", "all_inliers"])
+@pytest.mark.parametrize("model", MODELS)
+def test_adjoint_pixel_is_the_derivative_of_the_oracle_gradient(hostmath, model, scale):
+    """The per-pixel body of the differentiable LM's adjoint kernel (`adjoint_pixel`, host-compiled) against fp64
+    central differences of lambda . G of the ORACLE system, element by element over all five input planes: Jacobian rows,
+    Huber inlier and outlier branches (dw/do), confidences."""
+    h, w = 12, 16
+    cam, grav, up, lat, uconf, lconf = gt_and_estimate(model, h, w, 11)
+    nf = 3 + NUM_DIST[model]
+    lam = np.random.default_rng(2).normal(size=nf).astype(np.float32)
+    out = np.zeros((5, h, w), np.float32)
+    fp = lambda a: np.ascontiguousarray(a, np.float32).ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+    assert hostmath.gclm_host_math_adjoint(MODELS.index(model), h, w, fp(up), fp(lat), fp(uconf), fp(lconf), fp(cam), fp(grav),
+                                           fp(lam), scale, scale, out.ctypes.data_as(ctypes.POINTER(ctypes.c_float))) == 0
+    planes = [up.astype(np.float64), lat.astype(np.float64), uconf.astype(np.float64), lconf.astype(np.float64)]
+
+    def lam_G(pl):
+        G, _, _ = oracle.system(model, cam, grav, pl[0], pl[1][None], pl[2], pl[3], up_scale=scale, lat_scale=scale, dtype=np.float64)
+        return float(np.dot(lam.astype(np.float64), G))
+
+    eps = 1e-6
+    fd = np.zeros((5, h, w))
+    for k, (pi, ch) in enumerate([(0, 0), (0, 1), (1, None), (2, None), (3, None)]):
+        for y in range(h):
+            for x in range(w):
+                idx = (ch, y, x) if ch is not None else (..., y, x)
+                vals = []
+                for sgn in (+1, -1):
+                    pl = [p.copy() for p in planes]
+                    pl[pi][idx] += sgn * eps
+                    vals.append(lam_G(pl))
+                fd[k, y, x] = (vals[0] - vals[1]) / (2 * eps)
+    for k, name in enumerate(["up_x", "up_y", "latitude", "up_confidence", "latitude_confidence"]):
+        err = np.abs(out[k] - fd[k]).max() / max(np.abs(fd[k]).max(), 1e-12)
+        assert err < 1e-4, (name, err, np.abs(fd[k]).max())  # fp32 pixel math, measured <= 3e-5 of the plane maximum
+    if scale < 0.1:  # both Huber branches are exercised (latitude outliers have a zero derivative: w r = conf a sign(r))
+        assert (np.abs(fd[2]) == 0).any() and (np.abs(fd[2]) > 0).any()
