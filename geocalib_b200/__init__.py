@@ -13,11 +13,13 @@ not need a GPU, running the optimizer does.  There is no CPU fallback.
 from .autograd import differentiable_calibrate
 from .camera import BaseCamera, Pinhole, Radial, SimpleDivisional, SimpleRadial, camera_models
 from .extractor import calibrate_batch
+from .frontend import GraphedFrontEnd, install_frontend, uninstall_frontend
 from .gravity import Gravity
 from .lm_optimizer import B200LMOptimizer, LMOptimizer, get_trivial_estimation, install
 
 __all__ = [
     "BaseCamera", "Pinhole", "Radial", "SimpleDivisional", "SimpleRadial", "camera_models",
     "Gravity", "LMOptimizer", "B200LMOptimizer", "get_trivial_estimation", "install", "calibrate_batch", "differentiable_calibrate",
+    "GraphedFrontEnd", "install_frontend", "uninstall_frontend",
 ]
 __version__ = "0.1.0"
