@@ -8,11 +8,15 @@ and replays it from a static input buffer; `install_frontend(model)` puts it in 
 `GeoCalib.forward` (geocalib.py:106-119) calls the three modules.  Weights, arithmetic (fp32, cuDNN / cuBLAS kernels
 chosen by torch) and outputs are those of the reference; only the launch mechanism changes.
 
-One thing cannot be captured as it is: `NMF2D._build_bases` (modules.py:131-133) draws the random initial bases with
-the CPU generator and copies them to the device on every forward -- a pageable host-to-device copy inside the
-forward.  The front end swaps that one method for the same draw (uniform [0,1), normalised over D) from the CUDA
-generator, which torch advances correctly across graph replays; the distribution is the reference's, the stream of
-random numbers is not (it is not reproducible call to call in the reference either).
+Two statements of the reference cannot be captured as they are, both because they copy pageable host memory to the
+device inside the forward:
+  * `NMF2D._build_bases` (modules.py:131-133) draws the random initial bases with the CPU generator and copies them
+    over on every forward.  The front end swaps that one method for the same draw (uniform [0,1), normalised over D)
+    from the CUDA generator, which torch advances correctly across graph replays; the distribution is the
+    reference's, the stream of random numbers is not (it is not reproducible call to call in the reference either);
+  * `MSCAN.forward` (modules.py:560) permutes RGB -> BGR by indexing with the Python list [2, 1, 0], which torch turns
+    into a CPU index tensor + copy.  The backbone is therefore handed the image inside a proxy that answers exactly
+    that indexing expression with the equivalent `flip(1)` (bit-identical values) and forwards everything else.
 
 Not done here (the rest of 8f.4): hand-written kernels for the strip convolutions / NMF loop, channels-last, bf16.
 """
@@ -51,10 +55,29 @@ def use_device_bases(net: torch.nn.Module, build: Optional[Callable] = None) -> 
     return undo
 
 
-def cnn_forward(net: torch.nn.Module, image: torch.Tensor) -> Dict[str, torch.Tensor]:
-    """The CNN part of `GeoCalib.forward` (geocalib.py:106-110): image (B,3,H,W) -> the four decoder outputs."""
+class _ChannelFlipProxy:
+    """`proxy[:, [2, 1, 0], :, :]` -> `tensor.flip(1)` (modules.py:560 without the host-side index tensor)."""
+
+    def __init__(self, t: torch.Tensor):
+        assert t.dim() == 4 and t.shape[1] == 3
+        self._t = t
+
+    def __getitem__(self, key):
+        full = slice(None)
+        if isinstance(key, tuple) and len(key) == 4 and key[1] == [2, 1, 0] and key[0] == full and key[2] == full and key[3] == full:
+            return self._t.flip(1)
+        return self._t[key]
+
+    def __getattr__(self, name):
+        return getattr(self._t, name)
+
+
+def cnn_forward(net: torch.nn.Module, image: torch.Tensor, capturable: bool = False) -> Dict[str, torch.Tensor]:
+    """The CNN part of `GeoCalib.forward` (geocalib.py:106-110): image (B,3,H,W) -> the four decoder outputs.
+    `capturable`: hand the backbone the image through `_ChannelFlipProxy` (same values, no host-side index tensor)."""
     data = {"image": image}
-    features = {"hl": net.backbone(data)["features"], "ll": net.ll_enc(data)["features"]}
+    hl = net.backbone({"image": _ChannelFlipProxy(image)} if capturable else data)["features"]
+    features = {"hl": hl, "ll": net.ll_enc(data)["features"]}
     return net.perspective_decoder({"features": features})
 
 
@@ -67,9 +90,10 @@ class GraphedFrontEnd:
     (the engine reads them, `_post_process` interpolates them into new tensors).  `graph=False` runs the same code
     eagerly (CPU tests, debugging)."""
 
-    def __init__(self, net: torch.nn.Module, graph: bool = True, warmup: int = 3):
+    def __init__(self, net: torch.nn.Module, graph: bool = True, warmup: int = 3, capturable_eager: bool = False):
         self.net = net
         self.graph = graph
+        self.capturable_eager = capturable_eager  # graph=False only: run the eager modules through the capture-safe path
         self.warmup = warmup
         self._graphs: Dict[Tuple, Tuple[torch.cuda.CUDAGraph, torch.Tensor, Dict[str, torch.Tensor]]] = {}
         self.replays = 0
@@ -81,18 +105,18 @@ class GraphedFrontEnd:
         side.wait_stream(torch.cuda.current_stream(image.device))
         with torch.cuda.stream(side), torch.no_grad():
             for _ in range(self.warmup):
-                cnn_forward(self.net, static_in)
+                cnn_forward(self.net, static_in, capturable=True)
         torch.cuda.current_stream(image.device).wait_stream(side)
         g = torch.cuda.CUDAGraph()
         with torch.no_grad(), torch.cuda.graph(g):
-            static_out = cnn_forward(self.net, static_in)
+            static_out = cnn_forward(self.net, static_in, capturable=True)
         self.captures += 1
         return g, static_in, static_out
 
     def __call__(self, image: torch.Tensor) -> Dict[str, torch.Tensor]:
         if not self.graph:
             with torch.no_grad():
-                return cnn_forward(self.net, image)
+                return cnn_forward(self.net, image, capturable=self.capturable_eager)
         if not image.is_cuda:
             raise RuntimeError("GraphedFrontEnd: CUDA tensors only (graph=False runs the modules eagerly)")
         if self.net.training:

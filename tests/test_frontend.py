@@ -53,6 +53,12 @@ def test_frontend_wiring_equals_the_reference_forward_on_cpu(tmp_path):
         a, b = (res[k]._data, ref[k]._data) if hasattr(ref[k], "_data") else (res[k], ref[k])
         assert torch.equal(a, b), k
     assert front.replays == 0 and front.captures == 0
+    front.capturable_eager = True      # the capture-safe path (channel flip through the proxy): same bits
+    torch.manual_seed(11)
+    res = ex.calibrate(img)
+    for k in ref:
+        a, b = (res[k]._data, ref[k]._data) if hasattr(ref[k], "_data") else (res[k], ref[k])
+        assert torch.equal(a, b), k
     G.uninstall_frontend(ex)
     assert "forward" not in ex.model.__dict__ and all("_build_bases" not in m.__dict__ for m in FE.nmf_modules(ex.model))
     torch.manual_seed(11)
@@ -72,7 +78,7 @@ def test_graph_replay_equals_the_eager_cnn_and_redraws_the_bases(tmp_path):
     undo = FE.use_device_bases(net, fixed_bases)
     try:
         with torch.no_grad():
-            eager = {k: v.clone() for k, v in FE.cnn_forward(net, img).items()}
+            eager = {k: v.clone() for k, v in FE.cnn_forward(net, img).items()}   # the reference's statements, eager
         front = FE.GraphedFrontEnd(net)
         out1 = {k: v.clone() for k, v in front(img).items()}
         out2 = {k: v.clone() for k, v in front(img).items()}
