@@ -139,14 +139,18 @@ def test_divisional_clamped_root_pixels(hostmath, pack):
     assert_system_close(got, ref, tol=2e-4)  # Jacobians blow up next to the clamp (condition number ~1e10)
 
 
+ADJOINT_CASES = [(m, None) for m in MODELS] + [("simple_divisional", 0.0), ("simple_divisional", 0.45)]
+
+
 @pytest.mark.parametrize("scale", [1e-2, 0.2], ids=["default_scale_mostly_outliers", "all_inliers"])
-@pytest.mark.parametrize("model", MODELS)
-def test_adjoint_pixel_is_the_derivative_of_the_oracle_gradient(hostmath, model, scale):
+@pytest.mark.parametrize("model,k1", ADJOINT_CASES, ids=[f"{m}{'' if k is None else '_k1=' + str(k)}" for m, k in ADJOINT_CASES])
+def test_adjoint_pixel_is_the_derivative_of_the_oracle_gradient(hostmath, model, k1, scale):
     """The per-pixel body of the differentiable LM's adjoint kernel (`adjoint_pixel`, host-compiled) against fp64
     central differences of lambda . G of the ORACLE system, element by element over all five input planes: Jacobian rows,
-    Huber inlier and outlier branches (dw/do), confidences."""
+    Huber inlier and outlier branches (dw/do), confidences; for simple_divisional also the literal masked formulas
+    (k1 == 0: every pixel; k1 = 0.45: the clamped-root pixels in the corners)."""
     h, w = 12, 16
-    cam, grav, up, lat, uconf, lconf = gt_and_estimate(model, h, w, 11)
+    cam, grav, up, lat, uconf, lconf = gt_and_estimate(model, h, w, 11, k1=k1)
     nf = 3 + NUM_DIST[model]
     lam = np.random.default_rng(2).normal(size=nf).astype(np.float32)
     out = np.zeros((5, h, w), np.float32)
@@ -173,6 +177,8 @@ def test_adjoint_pixel_is_the_derivative_of_the_oracle_gradient(hostmath, model,
                 fd[k, y, x] = (vals[0] - vals[1]) / (2 * eps)
     for k, name in enumerate(["up_x", "up_y", "latitude", "up_confidence", "latitude_confidence"]):
         err = np.abs(out[k] - fd[k]).max() / max(np.abs(fd[k]).max(), 1e-12)
-        assert err < 1e-4, (name, err, np.abs(fd[k]).max())  # fp32 pixel math, measured <= 3e-5 of the plane maximum
+        # fp32 pixel math: measured <= 3e-5 of the plane maximum; next to the clamped root (k1 = 0.45: most pixels of this
+        # 12x16 fisheye) the formulas amplify rounding by ~1e3 (cf. test_divisional_clamped_root_pixels): 3e-4 measured
+        assert err < (1e-3 if k1 == 0.45 else 1e-4), (name, err, np.abs(fd[k]).max())
     if scale < 0.1:  # both Huber branches are exercised (latitude outliers have a zero derivative: w r = conf a sign(r))
         assert (np.abs(fd[2]) == 0).any() and (np.abs(fd[2]) > 0).any()
