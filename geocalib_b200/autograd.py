@@ -60,6 +60,27 @@ def sphere_plus(g: torch.Tensor, d: torch.Tensor) -> torch.Tensor:
     return torch.nn.functional.normalize(out, dim=-1)
 
 
+def perturbed_parameters(cam: torch.Tensor, grav: torch.Tensor, K: int, h: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """theta (+) +-h e_j for all n = 3 + K local parameters [g0 g1 | log f | k..]: cameras (2n,B,8) and gravities
+    (2n,B,3), ordered +e_0, -e_0, +e_1, ...  (the retraction of the LM update: sphere plus, f exp(delta), k + delta;
+    for the 1-parameter models delta k1 also lands in the k2 slot)."""
+    n, B = 3 + K, cam.shape[0]
+    d = torch.zeros((2 * n, B, n), device=cam.device, dtype=cam.dtype)
+    for j in range(n):
+        d[2 * j, :, j] = h
+        d[2 * j + 1, :, j] = -h
+    gr = sphere_plus(grav.repeat(2 * n, 1), d[..., :2].reshape(2 * n * B, 2)).reshape(2 * n, B, 3)
+    cm = cam.unsqueeze(0).repeat(2 * n, 1, 1)
+    cm[..., 2:4] = cm[..., 2:4] * torch.exp(d[..., 2:3])
+    if K >= 1:
+        cm[..., 6] = cm[..., 6] + d[..., 3]
+    if K == 2:
+        cm[..., 7] = cm[..., 7] + d[..., 4]
+    elif K == 1:
+        cm[..., 7] = cm[..., 6]
+    return cm.contiguous(), gr.contiguous()
+
+
 class _LMFixedPoint(torch.autograd.Function):
     @staticmethod
     def forward(ctx, up, lat, uconf, lconf, optimizer: LMOptimizer, fd_step: float):
@@ -98,25 +119,13 @@ class _LMFixedPoint(torch.autograd.Function):
                 g_loc[:, 3:5] = g_cam[:, 6:8]
 
         # ---- dG/dtheta by central differences of the fused pass ----
-        def G_at(delta):  # delta (B,n) in local parameters around (cam, grav)
-            gr = sphere_plus(grav, delta[:, :2])
-            cm = cam.clone()
-            cm[:, 2:4] = cam[:, 2:4] * torch.exp(delta[:, 2:3])
-            if K >= 1:
-                cm[:, 6] = cam[:, 6] + delta[:, 3]
-            if K == 2:
-                cm[:, 7] = cam[:, 7] + delta[:, 4]
-            elif K == 1:
-                cm[:, 7] = cm[:, 6]
-            G, _, _ = eng.system(name, up, lat, uconf, lconf, cm.contiguous(), gr.contiguous(), options=options, rpf_basis=False)
-            return G.double()
-
+        # all 2n perturbed parameter sets theta (+) +-h e_j in ONE batch of O(n B) torch work, then 2n system passes
         h = ctx.fd_step
-        A = torch.zeros((B, n, n), device=up.device, dtype=torch.float64)     # A[:, i, j] = dG_i / dtheta_j
-        for j in range(n):
-            d = torch.zeros((B, n), device=up.device, dtype=torch.float32)
-            d[:, j] = h
-            A[:, :, j] = (G_at(d) - G_at(-d)) / (2 * h)
+        cams, gravs = perturbed_parameters(cam, grav, K, h)              # (2n, B, 8), (2n, B, 3)
+        Gs = [eng.system(name, up, lat, uconf, lconf, cams[i], gravs[i], options=options, rpf_basis=False)[0]
+              for i in range(2 * n)]
+        Gs = torch.stack(Gs, 0).double()                                  # (2n, B, n): +h e_0, -h e_0, +h e_1, ...
+        A = ((Gs[0::2] - Gs[1::2]) / (2 * h)).permute(1, 2, 0).contiguous()   # A[:, i, j] = dG_i / dtheta_j
         lam = torch.linalg.solve(A.transpose(1, 2), g_loc.double()).float()   # (dG/dtheta)^-T dL/dtheta
         g_up, g_lat, g_uc, g_lc = eng.adjoint(name, up, lat, uconf, lconf, cam, grav, lam, options=options)
         # G here is J^T W r with r = obs - pred (the LM ascent direction): the fixed point moves by -A^-1 dG/dx

@@ -64,3 +64,31 @@ def test_differentiable_calibrate_checks_its_arguments_before_touching_a_gpu():
     opt2 = G.LMOptimizer({"camera_model": "pinhole", "use_log_focal": False}).eval()
     with pytest.raises(_lib.GclmError, match="log focal"):
         G.differentiable_calibrate(opt2, full)
+
+
+@pytest.mark.parametrize("K", [0, 1, 2])
+def test_perturbed_parameters_are_the_retraction_of_the_lm_update(K):
+    """theta (+) +-h e_j, batched: against the one-at-a-time formulation (sphere plus, f exp(delta), k + delta)."""
+    B, h, n = 3, 1e-3, 3 + K
+    g = unit(B, 4).float()
+    cam = torch.tensor([[640.0, 480, 500 + 10 * b, 510 + 10 * b, 320, 240, 0.1 * (K > 0), -0.02 * (K > 1)] for b in range(B)])
+    if K == 1:
+        cam[:, 7] = cam[:, 6]
+    cams, gravs = AG.perturbed_parameters(cam, g, K, h)
+    assert cams.shape == (2 * n, B, 8) and gravs.shape == (2 * n, B, 3) and cams.is_contiguous() and gravs.is_contiguous()
+    for j in range(n):
+        for s, sign in enumerate((+1.0, -1.0)):
+            d = torch.zeros(B, n)
+            d[:, j] = sign * h
+            gr = AG.sphere_plus(g, d[:, :2])
+            cm = cam.clone()
+            cm[:, 2:4] = cam[:, 2:4] * torch.exp(d[:, 2:3])
+            if K >= 1:
+                cm[:, 6] = cam[:, 6] + d[:, 3]
+            if K == 2:
+                cm[:, 7] = cam[:, 7] + d[:, 4]
+            elif K == 1:
+                cm[:, 7] = cm[:, 6]
+            assert torch.allclose(cams[2 * j + s], cm, rtol=0, atol=0), (j, sign)
+            assert torch.allclose(gravs[2 * j + s], gr, rtol=0, atol=1e-7), (j, sign)
+    assert torch.equal(cams[:, :, [0, 1, 4, 5]], cam[:, [0, 1, 4, 5]].expand(2 * n, B, 4))  # size / principal point untouched
