@@ -110,3 +110,39 @@ extern "C" int gclm_host_math_adjoint(int model, int H, int W, const float* up, 
   }
   return 0;
 }
+
+// ---- the solver-side pieces of the pass kernel's epilogue on the host: fixed-size damped-system solve, SPD inverse
+// (covariance), parameter updates.  n = 3, 4, 5. ----
+namespace {
+template <int N>
+int solve_n(const float* A_in, const float* b_in, float* x) {
+  float A[N][N], b[N];
+  for (int i = 0; i < N; i++) { b[i] = b_in[i]; for (int j = 0; j < N; j++) A[i][j] = A_in[i * N + j]; }
+  if (!cholesky_solve_fixed<N>(A, b)) return 1;
+  for (int i = 0; i < N; i++) x[i] = b[i];
+  return 0;
+}
+template <int N>
+int inverse_n(const float* A_in, float* out) {
+  float A[N][N], Ai[N][N];
+  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) A[i][j] = A_in[i * N + j];
+  if (!spd_inverse_fixed<N>(A, Ai)) return 1;
+  for (int i = 0; i < N; i++) for (int j = 0; j < N; j++) out[i * N + j] = Ai[i][j];
+  return 0;
+}
+}  // namespace
+
+extern "C" int gclm_host_math_solve(int n, const float* A, const float* b, float* x) {
+  switch (n) { case 3: return solve_n<3>(A, b, x); case 4: return solve_n<4>(A, b, x); case 5: return solve_n<5>(A, b, x); }
+  return -1;
+}
+extern "C" int gclm_host_math_spd_inverse(int n, const float* A, float* Ainv) {
+  switch (n) { case 3: return inverse_n<3>(A, Ainv); case 4: return inverse_n<4>(A, Ainv); case 5: return inverse_n<5>(A, Ainv); }
+  return -1;
+}
+// cam (8) and grav (3) are updated in place with the step delta = [g0 g1 | f | k..] (lm_optimizer.py:518-549)
+extern "C" void gclm_host_math_update(int model, float* cam, float* grav, const float* delta, int spherical, int log_focal) {
+  gravity_update(grav, delta[0], delta[1], spherical != 0);
+  focal_update(cam, delta[2], log_focal != 0);
+  if (model != PINHOLE) dist_update(model, cam, delta + 3);
+}

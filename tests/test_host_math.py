@@ -182,3 +182,78 @@ def test_adjoint_pixel_is_the_derivative_of_the_oracle_gradient(hostmath, model,
         assert err < (1e-3 if k1 == 0.45 else 1e-4), (name, err, np.abs(fd[k]).max())
     if scale < 0.1:  # both Huber branches are exercised (latitude outliers have a zero derivative: w r = conf a sign(r))
         assert (np.abs(fd[2]) == 0).any() and (np.abs(fd[2]) > 0).any()
+
+
+def _bind_solver(L):
+    fp = ctypes.POINTER(ctypes.c_float)
+    L.gclm_host_math_solve.restype = ctypes.c_int
+    L.gclm_host_math_solve.argtypes = [ctypes.c_int, fp, fp, fp]
+    L.gclm_host_math_spd_inverse.restype = ctypes.c_int
+    L.gclm_host_math_spd_inverse.argtypes = [ctypes.c_int, fp, fp]
+    L.gclm_host_math_update.restype = None
+    L.gclm_host_math_update.argtypes = [ctypes.c_int, fp, fp, fp, ctypes.c_int, ctypes.c_int]
+    return fp
+
+
+@pytest.mark.parametrize("n", [3, 4, 5])
+def test_fixed_size_cholesky_and_spd_inverse(hostmath, n):
+    """`cholesky_solve_fixed<N>` (the LM step) and `spd_inverse_fixed<N>` (the covariance) against numpy in fp64, on
+    systems with the scaling of real ones (gravity ~1e4, focal ~1e3, distortion ~1e2..1e4) and the LM damping."""
+    fp = _bind_solver(hostmath)
+    rng = np.random.default_rng(n)
+    for trial in range(20):
+        J = rng.normal(size=(200, n)) * np.array([100.0, 90.0, 30.0, 50.0, 150.0])[:n]
+        H = J.T @ J
+        H += np.diag(np.maximum(0.1 * np.diag(H), 1e-6))   # lm_optimizer.py:116-121
+        b = rng.normal(size=n) * np.sqrt(np.diag(H))
+        A32, b32 = np.ascontiguousarray(H, np.float32), np.ascontiguousarray(b, np.float32)
+        x, Ai = np.zeros(n, np.float32), np.zeros((n, n), np.float32)
+        assert hostmath.gclm_host_math_solve(n, A32.ctypes.data_as(fp), b32.ctypes.data_as(fp), x.ctypes.data_as(fp)) == 0
+        assert hostmath.gclm_host_math_spd_inverse(n, A32.ctypes.data_as(fp), Ai.ctypes.data_as(fp)) == 0
+        xr = np.linalg.solve(A32.astype(np.float64), b32.astype(np.float64))
+        Air = np.linalg.inv(A32.astype(np.float64))
+        cond = np.linalg.cond(A32.astype(np.float64))
+        assert np.abs(x - xr).max() <= 4e-7 * cond * np.abs(xr).max(), (trial, cond)
+        d = np.sqrt(np.diag(Air))
+        assert np.abs((Ai - Air) / np.outer(d, d)).max() <= 4e-7 * cond, (trial, cond)
+    # not positive definite: reported, not NaN
+    bad = np.diag([1.0, -1.0, 1.0, 1.0, 1.0][:n]).astype(np.float32)
+    out = np.zeros(n, np.float32)
+    assert hostmath.gclm_host_math_solve(n, bad.ctypes.data_as(fp), out.ctypes.data_as(fp), out.ctypes.data_as(fp)) == 1
+
+
+@pytest.mark.parametrize("model", MODELS)
+def test_parameter_updates_against_the_oracle_conventions(hostmath, model):
+    """gravity_update / focal_update / dist_update (lm_optimizer.py:518-549): sphere retraction, log-focal step with the
+    vfov clamp at [5, 150] degrees, distortion clamp, delta k1 mirrored into the k2 slot of one-parameter models."""
+    import torch
+
+    from geocalib_b200 import autograd as AG
+
+    fp = _bind_solver(hostmath)
+    K = NUM_DIST[model]
+    rng = np.random.default_rng(5)
+    for trial in range(50):
+        g = rng.normal(size=3)
+        g /= np.linalg.norm(g)
+        h = 480.0
+        cam = np.array([640, h, 500.0, 480.0, 320, 240, 0.1 if K else 0.0, -0.02 if K == 2 else (0.1 if K == 1 else 0.0)], np.float32)
+        delta = np.concatenate([rng.normal(size=2) * 0.2, rng.normal(size=1) * (3.0 if trial % 5 == 0 else 0.3),
+                                rng.normal(size=K) * (2.0 if trial % 7 == 0 else 0.1)]).astype(np.float32)
+        cam_new, g_new = cam.copy(), g.astype(np.float32).copy()
+        hostmath.gclm_host_math_update(MODELS.index(model), cam_new.ctypes.data_as(fp), g_new.ctypes.data_as(fp),
+                                       np.ascontiguousarray(np.concatenate([delta, np.zeros(2, np.float32)])).ctypes.data_as(fp), 1, 1)
+        g_ref = AG.sphere_plus(torch.from_numpy(g.astype(np.float32))[None], torch.from_numpy(delta[None, :2]))[0].numpy()
+        assert np.abs(g_new - g_ref).max() < 2e-6
+        fy = np.clip(np.exp(np.log(480.0) + float(delta[2])), h / 2 / np.tan(np.deg2rad(75.0)), h / 2 / np.tan(np.deg2rad(2.5)))
+        assert abs(cam_new[3] - fy) <= 2e-6 * fy and abs(cam_new[2] - fy * 500.0 / 480.0) <= 3e-6 * fy
+        lim = 3.0 if model == "simple_divisional" else 0.7
+        if K >= 1:
+            assert abs(cam_new[6] - np.clip(cam[6] + delta[3], -lim, lim)) < 1e-6
+        if K == 1:
+            assert cam_new[7] == cam_new[6]
+        if K == 2:
+            assert abs(cam_new[7] - np.clip(cam[7] + delta[4], -lim, lim)) < 1e-6
+        if K == 0:
+            assert cam_new[6] == 0 and cam_new[7] == 0
+        assert np.array_equal(cam_new[[0, 1, 4, 5]], cam[[0, 1, 4, 5]])
