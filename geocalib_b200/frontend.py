@@ -90,9 +90,11 @@ class GraphedFrontEnd:
     (the engine reads them, `_post_process` interpolates them into new tensors).  `graph=False` runs the same code
     eagerly (CPU tests, debugging)."""
 
-    def __init__(self, net: torch.nn.Module, graph: bool = True, warmup: int = 3, capturable_eager: bool = False):
+    def __init__(self, net: torch.nn.Module, graph: bool = True, warmup: int = 3, capturable_eager: bool = False,
+                 max_graphs: int = 8):
         self.net = net
         self.graph = graph
+        self.max_graphs = max_graphs  # every graph keeps its activations alive: least recently used shapes are dropped
         self.capturable_eager = capturable_eager  # graph=False only: run the eager modules through the capture-safe path
         self.warmup = warmup
         self._graphs: Dict[Tuple, Tuple[torch.cuda.CUDAGraph, torch.Tensor, Dict[str, torch.Tensor]]] = {}
@@ -113,6 +115,16 @@ class GraphedFrontEnd:
         self.captures += 1
         return g, static_in, static_out
 
+    def _lookup(self, key: Tuple, image: torch.Tensor):
+        """The graph of this input shape: most recently used last; capture on a miss, drop the oldest beyond the cap."""
+        entry = self._graphs.pop(key, None)
+        if entry is None:
+            while len(self._graphs) >= max(1, self.max_graphs):
+                self._graphs.pop(next(iter(self._graphs)))
+            entry = self._capture(image.contiguous())
+        self._graphs[key] = entry
+        return entry
+
     def __call__(self, image: torch.Tensor) -> Dict[str, torch.Tensor]:
         if not self.graph:
             with torch.no_grad():
@@ -121,10 +133,7 @@ class GraphedFrontEnd:
             raise RuntimeError("GraphedFrontEnd: CUDA tensors only (graph=False runs the modules eagerly)")
         if self.net.training:
             raise RuntimeError("GraphedFrontEnd is an inference path: put the network in eval mode")
-        key = (image.device.index, tuple(image.shape), image.dtype)
-        if key not in self._graphs:
-            self._graphs[key] = self._capture(image.contiguous())
-        g, static_in, static_out = self._graphs[key]
+        g, static_in, static_out = self._lookup((image.device.index, tuple(image.shape), image.dtype), image)
         static_in.copy_(image)
         g.replay()
         self.replays += 1

@@ -68,6 +68,21 @@ def test_frontend_wiring_equals_the_reference_forward_on_cpu(tmp_path):
         FE.GraphedFrontEnd(ex.model)(img[None])
 
 
+def test_graph_cache_is_bounded_and_least_recently_used():
+    """Pure host logic (no reference, no GPU): one entry per shape, capped, oldest dropped first."""
+    from geocalib_b200 import frontend as FE
+
+    front = FE.GraphedFrontEnd(torch.nn.Identity(), max_graphs=2)
+    made = []
+    front._capture = lambda image: made.append(tuple(image.shape)) or ("graph", image, {"shape": tuple(image.shape)})
+    a, b, c = torch.zeros(1, 3, 32, 32), torch.zeros(1, 3, 64, 32), torch.zeros(2, 3, 32, 32)
+    key = lambda t: (None, tuple(t.shape), t.dtype)
+    for t in (a, b, a, c, a, b):            # a, b captured; a re-used; c evicts b; a re-used; b captured again, evicts c
+        assert front._lookup(key(t), t)[2]["shape"] == tuple(t.shape)
+    assert made == [tuple(a.shape), tuple(b.shape), tuple(c.shape), tuple(b.shape)]
+    assert list(front._graphs) == [key(a), key(b)]
+
+
 @pytest.mark.gpu
 def test_graph_replay_equals_the_eager_cnn_and_redraws_the_bases(tmp_path):
     from geocalib_b200 import frontend as FE
