@@ -136,7 +136,8 @@ def differentiable_calibrate(optimizer: LMOptimizer, data: Dict[str, torch.Tenso
     """LM calibration whose outputs carry gradients w.r.t. the four field tensors.
 
     Returns (camera_data (B,8), gravity (B,3), final_cost (B,), stop_at (B,)); `camera_data[:, 2:4]` (focal),
-    `[:, 6:8]` (distortion) and `gravity` are differentiable.  Run enough iterations to converge (the gradient is
+    `[:, 6:8]` (distortion) and `gravity` are differentiable.  `final_cost` and `stop_at` are
+    reported values: a gradient arriving on them is NOT propagated (use the parameters in the loss).  Run enough iterations to converge (the gradient is
     that of the fixed point): `num_steps` >= 20 with early stop is the usual choice."""
     for k in ("up_field", "latitude_field", "up_confidence", "latitude_confidence"):
         if k not in data:
