@@ -142,6 +142,9 @@ def differentiable_calibrate(optimizer: LMOptimizer, data: Dict[str, torch.Tenso
     for k in ("up_field", "latitude_field", "up_confidence", "latitude_confidence"):
         if k not in data:
             raise _lib.GclmError(f"differentiable_calibrate needs {k!r} (both fields with confidences)")
+    extra = [k for k in ("prior_focal", "prior_gravity", "prior_dist", "scales", "packed_fields") if k in data]
+    if extra:  # they change which parameters are free / the initial estimate: not wired into the backward yet
+        raise _lib.GclmError(f"differentiable_calibrate: {extra} are not supported (all of gravity, focal, distortion are estimated)")
     if optimizer.shared_intrinsics:
         raise _lib.GclmError("differentiable_calibrate: per-image intrinsics only")
     c = optimizer.conf

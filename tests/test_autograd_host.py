@@ -57,6 +57,8 @@ def test_differentiable_calibrate_checks_its_arguments_before_touching_a_gpu():
     with pytest.raises(_lib.GclmError, match="up_confidence"):
         G.differentiable_calibrate(opt, f)
     full = dict(f, up_confidence=torch.ones(1, 8, 8), latitude_confidence=torch.ones(1, 8, 8))
+    with pytest.raises(_lib.GclmError, match="prior_focal"):   # priors would silently be ignored otherwise
+        G.differentiable_calibrate(opt, dict(full, prior_focal=torch.tensor([300.0])))
     opt.shared_intrinsics = True
     with pytest.raises(_lib.GclmError, match="per-image"):
         G.differentiable_calibrate(opt, full)
